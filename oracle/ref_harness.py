@@ -163,7 +163,8 @@ def run_reference(model, ctl, clicks=()):
         raise ValueError(ev)
 
     ref.plot = plot
-    ref.prn_upd = lambda *a: None
+    messages = []
+    ref.prn_upd = lambda *a: messages.append("".join(str(o) for o in a))
     win = _Window(ctl.csr_option == "CSR")
     res = ref.calcDisp(m.elNodes, m.nocoord.copy(), m.fixdof, m.movdof, modf, m.materialbyElement, stm, row, col,
                        glv, ctl.nstep, ctl.iterat_max, ctl.error_max, ctl.relax, ctl.scale_re, ctl.scale_up,
@@ -175,4 +176,24 @@ def run_reference(model, ctl, clicks=()):
             "un", "crip", "peeqplot", "pplot", "svmplot", "triaxplot", "ecrplot", "csrplot", "fail", "nocoord_old"]
     d = dict(zip(keys, res))
     d.update(stm=stm, row=row, col=col, glv=glv, modf=modf, V=V, loadsum=(lsx, lsy, lsz), x=x)
+    d["messages"] = messages
+    d["iters"] = iterations_per_step(messages)
     return d
+
+
+def iterations_per_step(messages):
+    """Newton iterations of every load step, read off the reference's own progress
+    lines ("Step: n" / "Iteration: k, Error: e", fcVM.py:1315, 1344, 1455).  A restart
+    resets the counter (fcVM.py:1484); the last value printed before the next "Step"
+    is the count the step ended with."""
+    its, cur = [], None
+    for msg in messages:
+        if msg.startswith("Step:") and "Load level" not in msg:
+            if cur is not None:
+                its.append(cur)
+            cur = 0
+        elif msg.startswith("Iteration:"):
+            cur = int(msg.split(",")[0].split(":")[1])
+    if cur is not None:
+        its.append(cur)
+    return its

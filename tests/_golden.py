@@ -1,0 +1,54 @@
+"""Loaders for tests/golden/*.npz (written by oracle/gen_golden.py from the unmodified reference)."""
+import os
+
+import numpy as np
+
+from fcvm_workbench_b200.control import Control
+from fcvm_workbench_b200.model import Model
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ANALYSES = ("tensile", "cube2_platen", "cube2_force", "cube2_gnly")
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
+
+
+def model_of(z) -> Model:
+    ne = len(z["m_elNodes"])
+    fix = {int(d): float(v) for d, v in zip(z["m_fix_dof"], z["m_fix_val"])}
+    return Model(name=str(z["m_name"]), elNodes=z["m_elNodes"], nocoord=z["m_nocoord"], fix=fix,
+                 fixdof=z["m_fixdof"], movdof=z["m_movdof"],
+                 materialbyElement=np.tile(z["m_materialbyElement"][0], (ne, 1)), noce=z["m_noce"],
+                 loadfaces=z["m_loadfaces"], pressure=z["m_pressure"], loadvertices=z["m_loadvertices"],
+                 vertexloads=z["m_vertexloads"], loadedges=z["m_loadedges"], edgeloads=z["m_edgeloads"],
+                 loadfaces_uni=z["m_loadfaces_uni"], faceloads=z["m_faceloads"])
+
+
+def control_of(z) -> Control:
+    kw = {}
+    for f in Control.__dataclass_fields__:
+        v = z["c_" + f]
+        kw[f] = v.item() if v.dtype.kind in "fiu" else str(v)
+    return Control(**kw)
+
+
+def clicks_of(z):
+    out = []
+    for s in z["clicks"]:
+        s = str(s)
+        if not s:
+            continue
+        if ":" in s:
+            a, b = s.split(":")
+            out.append((a, float(b)))
+        else:
+            out.append(s)
+    return out
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))

@@ -1,0 +1,135 @@
+"""The CPU oracle against fixtures produced by the UNMODIFIED reference.
+
+This is the pin that lets the oracle stand in for the reference on the GPU box
+(where /root/reference does not exist).  Tolerances: 1e-12 relative for single
+kernel calls (same arithmetic, different compiler), 1e-9 for whole analyses
+(hundreds of solves with a different -- equally backward-stable -- direct solver).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as scsp
+
+from _golden import ANALYSES, clicks_of, control_of, load, model_of, rel
+
+
+@pytest.mark.parametrize("name", ANALYSES)
+def test_load_stepping_matches_reference(oracle, name):
+    z = load(name)
+    m, c = model_of(z), control_of(z)
+    gsm = []
+    o = oracle.calcDisp(m, c, clicks=clicks_of(z), gsm_out=gsm)
+    assert list(o["iters"]) == list(z["r_iters"]), "Newton iterations per step differ"
+    for k in ("lout", "un", "peeqplot", "pplot", "svmplot", "triaxplot", "ecrplot", "csrplot"):
+        assert rel(o[k], z["r_" + k]) < 1e-9, k
+    for k in ("displacements", "disp_el", "stresses", "peeq", "sigmises", "csr"):
+        assert rel(o[k], z["r_" + k]) < 1e-8, k
+    if name == "tensile":                      # the symmetric cubes have exact ties in argmax(csr)
+        assert np.array_equal(o["crip"], z["r_crip"])
+    # CSC pattern of the assembled lower triangle: bit-exact (elastic matrix, before any tangent update)
+    g = gsm[0]
+    assert np.array_equal(g.indptr, z["r_gsm_indptr"])
+    assert np.array_equal(g.indices, z["r_gsm_indices"])
+    if name != "cube2_gnly":
+        assert rel(g.data, z["r_gsm_data"]) < 1e-12
+
+
+def test_tensile_rows_match_committed_out_file(oracle):
+    """Rows of the reference's own ``output files/tensile.out`` (3 significant digits)."""
+    z = load("tensile")
+    o = oracle.calcDisp(model_of(z), control_of(z), clicks=clicks_of(z))
+    # (Gauss point, load, disp, peeq, pressure, svmises, triax, eps_cr, csr_max) -- tensile.out lines 14-31
+    rows = {
+        1: (0, 1.00e-01, 1.00e-02, 0.00e+00, 3.33e+01, 1.00e+02, 6.67e-02, 3.73e-01, 0.00e+00),
+        3: (0, 3.00e-01, 3.00e-02, 0.00e+00, 1.00e+02, 3.00e+02, 2.00e-01, 3.05e-01, 0.00e+00),
+        7: (20, 5.00e-01, 5.85e-02, 8.16e-04, 1.67e+02, 5.00e+02, 3.33e-01, 2.50e-01, 3.27e-03),
+        12: (20, 5.00e-01, 1.29e-01, 6.89e-03, 1.67e+02, 5.00e+02, 3.33e-01, 2.50e-01, 2.76e-02),
+        16: (20, 5.00e-01, 2.60e-01, 1.78e-02, 1.67e+02, 5.00e+02, 3.33e-01, 2.50e-01, 7.12e-02),
+    }
+    for i, (gp, load_, disp, peeq, p, svm, tr, ecr, csr) in rows.items():
+        assert int(o["crip"][i]) == gp
+        got = (o["lout"][i], o["un"][i], o["peeqplot"][i], o["pplot"][i], o["svmplot"][i], o["triaxplot"][i],
+               o["ecrplot"][i], o["csrplot"][i])
+        for g, w in zip(got, (load_, disp, peeq, p, svm, tr, ecr, csr)):
+            assert float(f"{g:.2e}") == pytest.approx(w, abs=1e-12, rel=1.1e-2), (i, g, w)
+    xgp = o["x"][20]
+    assert [float(f"{v:.2e}") for v in xgp] == [9.31, 7.24, 9.31]
+
+
+def test_element_matrices_and_assembly(oracle):
+    z = load("kernels")
+    m = model_of(z)
+    g = z["grav"]
+    out = oracle.calcGSM(m.elNodes, m.nocoord, m.materialbyElement, m.fix, g[0], g[1], g[2], m.loadfaces, m.pressure,
+                         m.loadvertices, m.vertexloads, m.loadedges, m.edgeloads, m.loadfaces_uni, m.faceloads,
+                         return_esm=True)
+    stm, row, col, glv, modf, V, _, _, _, ne, nn, x, esm = out
+    for e in range(ne):
+        assert rel(esm[e], z["r_esm"][e]) < 1e-12
+    assert np.array_equal(row, z["r_row"]) and np.array_equal(col, z["r_col"])
+    assert rel(stm, z["r_stm"]) < 1e-12
+    assert rel(glv, z["r_glv"]) < 1e-12 and rel(modf, z["r_modf"]) < 1e-12
+    assert rel(x, z["r_x"]) < 1e-13 and abs(V - float(z["r_V"])) < 1e-10 * abs(float(z["r_V"]))
+
+
+@pytest.mark.parametrize("tag,LD", [("sm", False), ("ld", True)])
+def test_update_stress_load(oracle, tag, LD):
+    z = load("kernels")
+    m = model_of(z)
+    ne, nn = m.ne, m.nn
+    sig_new, sig_test, qin = np.zeros(24 * ne), np.zeros(24 * ne), np.zeros(3 * nn)
+    pgp = np.full(4 * ne, False)
+    oracle.update_stress_load(None, m.elNodes, m.nocoord, m.materialbyElement, z[f"{tag}_sy"], z[f"{tag}_disp"],
+                              z[f"{tag}_du"], z[f"{tag}_sig"], sig_new, sig_test, qin, float(z[f"{tag}_Et_E"]), LD,
+                              pgp)
+    assert np.array_equal(pgp, z[f"r_{tag}_pgp"])
+    assert 0 < pgp.sum() < pgp.size, "fixture must mix elastic and plastic Gauss points"
+    assert rel(sig_test, z[f"r_{tag}_sig_test"]) < 1e-12
+    assert rel(sig_new, z[f"r_{tag}_sig_new"]) < 1e-12
+    assert rel(qin, z[f"r_{tag}_qin"]) < 1e-12
+
+
+def test_tangent_stiffness(oracle):
+    z = load("kernels")
+    m = model_of(z)
+    g = z["grav"]
+    stm, _, _, row, col, glv, modf = oracle.calcTSM(
+        8, m.elNodes, m.nocoord, m.materialbyElement, m.fix, g[0], g[1], g[2], m.loadfaces, m.pressure,
+        m.loadvertices, m.vertexloads, m.loadedges, m.edgeloads, m.loadfaces_uni, m.faceloads, z["ld_disp"],
+        z["ld_du"], z["ld_sig"], z["r_ld_pgp"], float(z["ld_Et_E"]))
+    assert np.array_equal(row, z["r_tsm_row"]) and np.array_equal(col, z["r_tsm_col"])
+    assert rel(stm, z["r_tsm_stm"]) < 1e-11
+    assert rel(glv, z["r_tsm_glv"]) < 1e-12 and rel(modf, z["r_tsm_modf"]) < 1e-11
+
+
+def test_peeq_csr_and_nodal_mapping(oracle):
+    z = load("kernels")
+    m = model_of(z)
+    ne = m.ne
+    sy = z["sm_sy"].copy()
+    peeq, csr = z["pq_peeq0"].copy(), z["pq_csr0"].copy()
+    triax, pres, svm, ecr = (np.zeros(4 * ne) for _ in range(4))
+    oracle.update_PEEQ_CSR(ne, m.materialbyElement, z["r_sm_sig_test"], z["r_sm_sig_new"], sy, float(z["pq_ult"]),
+                           peeq, csr, triax, pres, svm, ecr, float(z["sm_Et_E"]))
+    for a, k in ((sy, "sy"), (peeq, "peeq"), (csr, "csr"), (triax, "triax"), (pres, "pressure"),
+                 (svm, "sigmises"), (ecr, "ecr")):
+        assert rel(a, z["r_pq_" + k]) < 1e-12, k
+    for averaged, k in ((False, "max"), (True, "avg")):
+        t = oracle.mapStresses(averaged, m.elNodes, m.nocoord, z["r_sm_sig_new"], peeq, svm, csr, m.noce, 180.0)
+        for a, f in zip(t, ("stress", "peeq", "csr", "svm", "triax")):
+            assert rel(a, z[f"r_map_{k}_{f}"]) < 1e-12, (k, f)
+
+
+def test_oracle_against_live_reference_when_present(oracle):
+    """In the build container the unmodified reference itself is run beside the oracle."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference sources not present on this machine (golden fixtures are the pin)")
+    from fcvm_workbench_b200.control import Control
+    from fcvm_workbench_b200.mesh import cube_model
+    m = cube_model(2, mode="punch", top_disp=0.08, nxyz=(3, 2, 2))
+    c = Control(sig_yield=200.0, nstep=6, error_max=1e-6, target_LF=2.0, Et_E=0.0)
+    d = rh.run_reference(m, c)
+    o = oracle.calcDisp(m, c)
+    assert list(o["iters"]) == list(d["iters"])
+    assert rel(o["lout"], d["lout"]) < 1e-9 and rel(o["un"], d["un"]) < 1e-9
+    assert rel(o["stresses"], d["stresses"]) < 1e-8
