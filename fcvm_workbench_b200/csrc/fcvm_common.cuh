@@ -1,0 +1,301 @@
+// Shared definitions of the fcvm_b200 CUDA library (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fcvm_b200.h"
+
+namespace fcvm {
+
+void set_error(const char *fmt, ...);
+
+#define FCVM_CUDA(call)                                                                         \
+  do {                                                                                          \
+    cudaError_t err__ = (call);                                                                 \
+    if (err__ != cudaSuccess) {                                                                 \
+      fcvm::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+      return FCVM_E_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+#define FCVM_CHECK(cond, code, ...)   \
+  do {                                \
+    if (!(cond)) {                    \
+      fcvm::set_error(__VA_ARGS__);   \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define FCVM_TRY(expr)            \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != FCVM_OK) return rc__; \
+  } while (0)
+
+constexpr int SELL_C = 32;           // rows per SELL slice = one warp
+constexpr int SELL_SIGMA = 4096;     // sorting window (rows)
+constexpr int RED_BLOCKS = 592;      // 4 x 148 SMs: fixed shape of every two-stage reduction
+constexpr int RED_THREADS = 256;
+constexpr int NUM_PROFILE = 5;
+
+// Gauss points of the 10-node tetrahedron (fcVM.py:589-596)
+constexpr double GP_A = 0.138196601125011;
+constexpr double GP_B = 0.585410196624968;
+constexpr double GP_W = 0.041666666666667;
+
+struct Profile {
+  double ms[NUM_PROFILE];
+  int64_t launches[NUM_PROFILE];
+};
+
+}  // namespace fcvm
+
+struct fcvm_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // fcvm_timer_*
+  cudaEvent_t pev0 = nullptr, pev1 = nullptr;    // profiling
+  int profiling = 0;
+  fcvm::Profile prof{};
+  int64_t launches = 0;
+
+  // mesh
+  int64_t ne = 0, nn = 0;
+  double E = 0, nu = 0, density = 0;
+  int32_t *conn = nullptr;      // [10][ne] zero-based
+  double *xyz = nullptr;        // [nn][3]
+  int32_t *n2e_ptr = nullptr;   // [nn+1]
+  int32_t *n2e_idx = nullptr;   // [10*ne]  e*10+j, ascending e within a node
+  double *elv = nullptr;        // [ne][30] element vectors (scratch of the gather)
+
+  // constraints
+  uint8_t *fixmask = nullptr;   // [3nn]
+  double *fixval = nullptr;     // [3nn]
+  double *movmask = nullptr;    // [3nn] 1.0 where a non-zero value is prescribed
+  bool have_bcs = false;
+
+  // Gauss-point state and named nodal buffers
+  void *buf[FCVM_BUF_COUNT] = {nullptr};
+
+  // matrix: block-SELL
+  int64_t nslices = 0;          // ceil(nn/32)
+  int64_t nblk_real = 0;        // distinct (row node, col node) pairs
+  int64_t nblk_stored = 0;      // incl. padding = 32 * sum(slice widths)
+  int32_t *slice_ptr = nullptr; // [nslices+1] in units of block-columns (x32 blocks)
+  int32_t *slot_node = nullptr; // [nslices*32] node of SELL slot, -1 = padding row
+  int32_t *node_slot = nullptr; // [nn]
+  int32_t *colidx = nullptr;    // [nblk_stored] block column (node)
+  double *vals = nullptr;       // [nblk_stored/32][9][32]
+  uint32_t *blk_first = nullptr;// [nblk_stored] first contribution in src
+  uint32_t *blk_cnt = nullptr;  // [nblk_stored] number of contributions (0 for padding)
+  uint32_t *src = nullptr;      // [100*ne] ((pair*ne + e) << 1) | transpose
+  int32_t *diag_pos = nullptr;  // [nn] position of the diagonal block
+  int32_t *row_first = nullptr; // [nn+1] CSR-like row pointer over real blocks (for export)
+  int32_t *row_cols = nullptr;  // [nblk_real] sorted block columns (for export)
+  double *cooK = nullptr;       // [55][ne][9] element stiffness blocks (lower block triangle)
+  double *minv = nullptr;       // [nn][9] inverse diagonal blocks
+  bool assembled = false;
+
+  // PCG work vectors
+  double *pcg_r = nullptr, *pcg_z = nullptr, *pcg_p = nullptr, *pcg_q = nullptr;
+
+  // reductions
+  double *red_part = nullptr;   // [8][RED_BLOCKS]
+  double *red_out = nullptr;    // [16] device scalars
+  unsigned int *red_counter = nullptr;
+  double *h_scalars = nullptr;  // pinned [16]
+  int64_t *d_arg = nullptr;     // argmax result
+  int64_t *d_arg_part = nullptr;// [RED_BLOCKS] argmax partials
+  int64_t *h_arg = nullptr;     // pinned
+
+  // multi-GPU
+  void *nccl_comm = nullptr;
+  int rank = 0, world = 1;
+  double *dof_weight = nullptr; // [3nn] 1/multiplicity (nullptr = 1)
+  int64_t n_if_local = 0, n_if_global = 0;
+  int32_t *if_node = nullptr;   // [n_if_local]
+  int32_t *if_slot = nullptr;   // [n_if_local]
+  double *if_buf = nullptr;     // [3*n_if_global]
+
+  // host staging / device scratch of fcvm_host_*
+  double *stage = nullptr;
+  int64_t stage_n = 0;
+  double *h_du = nullptr, *h_disp = nullptr, *h_qin = nullptr;
+  double *diag9 = nullptr;      // [3][nn][3] assembled diagonal blocks, row-wise
+};
+
+namespace fcvm {
+
+inline int grid_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// profiling wrapper: records events around a launch when enabled
+struct ProfScope {
+  fcvm_ctx *c;
+  int which;
+  ProfScope(fcvm_ctx *ctx, int w) : c(ctx), which(w) {
+    if (c->profiling) cudaEventRecord(c->pev0, c->stream);
+  }
+  ~ProfScope() {
+    if (c->profiling) {
+      cudaEventRecord(c->pev1, c->stream);
+      cudaEventSynchronize(c->pev1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->pev0, c->pev1);
+      c->prof.ms[which] += ms;
+      c->prof.launches[which] += 1;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Device helpers: 10-node tetrahedron at Gauss point GP (0..3).
+// Local derivative table of fcVM.py:390-424 with the Gauss coordinates folded in at
+// compile time; zero entries vanish from the generated code.
+// ---------------------------------------------------------------------------------------
+template <int GP>
+struct GaussPt {
+  static constexpr double xi = (GP == 1) ? GP_B : GP_A;
+  static constexpr double et = (GP == 2) ? GP_B : GP_A;
+  static constexpr double ze = (GP == 3) ? GP_B : GP_A;
+  static constexpr double a4 = 1.0 - 4.0 * (1.0 - xi - et - ze);
+};
+
+// sum_k v[k][i] * dN[j][k]  for j = 0,1,2  (v: 10 nodal 3-vectors)  -> out[i][j]
+template <int GP>
+__device__ __forceinline__ void local_gradient(const double (&v)[10][3], double (&out)[3][3]) {
+  constexpr double xi = GaussPt<GP>::xi, et = GaussPt<GP>::et, ze = GaussPt<GP>::ze, a4 = GaussPt<GP>::a4;
+  constexpr double d01 = 4.0 * xi - 1.0, d04 = 4.0 * (1.0 - 2.0 * xi - et - ze);
+  constexpr double d12 = 4.0 * et - 1.0, d16 = 4.0 * (1.0 - xi - 2.0 * et - ze);
+  constexpr double d23 = 4.0 * ze - 1.0, d27 = 4.0 * (1.0 - xi - et - 2.0 * ze);
+  constexpr double x4 = 4.0 * xi, e4 = 4.0 * et, z4 = 4.0 * ze;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    // xi-derivative: nodes 0,1,4,5,6,7,8
+    out[i][0] = a4 * v[0][i] + d01 * v[1][i] + d04 * v[4][i] + e4 * (v[5][i] - v[6][i]) + z4 * (v[8][i] - v[7][i]);
+    // eta-derivative: nodes 0,2,4,5,6,7,9
+    out[i][1] = a4 * v[0][i] + d12 * v[2][i] + x4 * (v[5][i] - v[4][i]) + d16 * v[6][i] + z4 * (v[9][i] - v[7][i]);
+    // zeta-derivative: nodes 0,3,4,6,7,8,9
+    out[i][2] = a4 * v[0][i] + d23 * v[3][i] - x4 * v[4][i] - e4 * v[6][i] + d27 * v[7][i] + x4 * v[8][i] +
+                e4 * v[9][i];
+  }
+}
+
+// F[k][i] += sum_j T[i][j] * dN[j][k]  (transpose of local_gradient, same constants)
+template <int GP>
+__device__ __forceinline__ void scatter_gradient(const double (&T)[3][3], double (&F)[10][3]) {
+  constexpr double xi = GaussPt<GP>::xi, et = GaussPt<GP>::et, ze = GaussPt<GP>::ze, a4 = GaussPt<GP>::a4;
+  constexpr double d01 = 4.0 * xi - 1.0, d04 = 4.0 * (1.0 - 2.0 * xi - et - ze);
+  constexpr double d12 = 4.0 * et - 1.0, d16 = 4.0 * (1.0 - xi - 2.0 * et - ze);
+  constexpr double d23 = 4.0 * ze - 1.0, d27 = 4.0 * (1.0 - xi - et - 2.0 * ze);
+  constexpr double x4 = 4.0 * xi, e4 = 4.0 * et, z4 = 4.0 * ze;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double t0 = T[i][0], t1 = T[i][1], t2 = T[i][2];
+    F[0][i] += a4 * (t0 + t1 + t2);
+    F[1][i] += d01 * t0;
+    F[2][i] += d12 * t1;
+    F[3][i] += d23 * t2;
+    F[4][i] += d04 * t0 - x4 * (t1 + t2);
+    F[5][i] += e4 * t0 + x4 * t1;
+    F[6][i] += d16 * t1 - e4 * (t0 + t2);
+    F[7][i] += d27 * t2 - z4 * (t0 + t1);
+    F[8][i] += z4 * t0 + x4 * t2;
+    F[9][i] += z4 * t1 + e4 * t2;
+  }
+}
+
+// dN[j][k] as a compile-time constant
+template <int GP>
+__device__ __forceinline__ constexpr double dN(int j, int k) {
+  constexpr double xi = GaussPt<GP>::xi, et = GaussPt<GP>::et, ze = GaussPt<GP>::ze, a4 = GaussPt<GP>::a4;
+  if (j == 0) {
+    switch (k) {
+      case 0: return a4;
+      case 1: return 4.0 * xi - 1.0;
+      case 4: return 4.0 * (1.0 - 2.0 * xi - et - ze);
+      case 5: return 4.0 * et;
+      case 6: return -4.0 * et;
+      case 7: return -4.0 * ze;
+      case 8: return 4.0 * ze;
+      default: return 0.0;
+    }
+  } else if (j == 1) {
+    switch (k) {
+      case 0: return a4;
+      case 2: return 4.0 * et - 1.0;
+      case 4: return -4.0 * xi;
+      case 5: return 4.0 * xi;
+      case 6: return 4.0 * (1.0 - xi - 2.0 * et - ze);
+      case 7: return -4.0 * ze;
+      case 9: return 4.0 * ze;
+      default: return 0.0;
+    }
+  } else {
+    switch (k) {
+      case 0: return a4;
+      case 3: return 4.0 * ze - 1.0;
+      case 4: return -4.0 * xi;
+      case 6: return -4.0 * et;
+      case 7: return 4.0 * (1.0 - xi - et - 2.0 * ze);
+      case 8: return 4.0 * xi;
+      case 9: return 4.0 * et;
+      default: return 0.0;
+    }
+  }
+}
+
+// shape functions N_k at Gauss point GP (fcVM.py:364-380)
+template <int GP>
+__device__ __forceinline__ constexpr double shpN(int k) {
+  constexpr double xi = GaussPt<GP>::xi, et = GaussPt<GP>::et, ze = GaussPt<GP>::ze;
+  constexpr double a = 1.0 - xi - et - ze;
+  switch (k) {
+    case 0: return (2.0 * a - 1.0) * a;
+    case 1: return xi * (2.0 * xi - 1.0);
+    case 2: return et * (2.0 * et - 1.0);
+    case 3: return ze * (2.0 * ze - 1.0);
+    case 4: return 4.0 * xi * a;
+    case 5: return 4.0 * xi * et;
+    case 6: return 4.0 * et * a;
+    case 7: return 4.0 * ze * a;
+    case 8: return 4.0 * xi * ze;
+    default: return 4.0 * et * ze;
+  }
+}
+
+// Jacobian xs[i][j] = d x_i / d xi_j, its determinant and inverse xsi (fcVM.py:428-453):
+// dshpg[m][k] = sum_j xsi[j][m] * dN[j][k]
+template <int GP>
+__device__ __forceinline__ double jacobian(const double (&X)[10][3], double (&xsi)[3][3]) {
+  double xs[3][3];
+  local_gradient<GP>(X, xs);
+  double xsj = (xs[0][0] * xs[1][1] * xs[2][2] - xs[0][0] * xs[1][2] * xs[2][1] + xs[0][2] * xs[1][0] * xs[2][1] -
+                xs[0][2] * xs[1][1] * xs[2][0] + xs[0][1] * xs[1][2] * xs[2][0] - xs[0][1] * xs[1][0] * xs[2][2]);
+  double inv = 1.0 / xsj;
+  xsi[0][0] = (xs[1][1] * xs[2][2] - xs[2][1] * xs[1][2]) * inv;
+  xsi[0][1] = (xs[0][2] * xs[2][1] - xs[0][1] * xs[2][2]) * inv;
+  xsi[0][2] = (xs[0][1] * xs[1][2] - xs[0][2] * xs[1][1]) * inv;
+  xsi[1][0] = (xs[1][2] * xs[2][0] - xs[1][0] * xs[2][2]) * inv;
+  xsi[1][1] = (xs[0][0] * xs[2][2] - xs[0][2] * xs[2][0]) * inv;
+  xsi[1][2] = (xs[1][0] * xs[0][2] - xs[0][0] * xs[1][2]) * inv;
+  xsi[2][0] = (xs[1][0] * xs[2][1] - xs[2][0] * xs[1][1]) * inv;
+  xsi[2][1] = (xs[2][0] * xs[0][1] - xs[0][0] * xs[2][1]) * inv;
+  xsi[2][2] = (xs[0][0] * xs[1][1] - xs[1][0] * xs[0][1]) * inv;
+  return xsj;
+}
+
+// block-level deterministic sum: fixed tree over the warp, then over warps in order
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace fcvm

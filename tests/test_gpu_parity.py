@@ -1,0 +1,296 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden
+fixtures.  Tolerances are the ones BASELINE.json's north_star states:
+
+* element stiffness and internal force: 1e-10 relative
+* elastic/plastic classification identical away from a 1e-8 (relative) yield-surface band
+* CSC pattern / dof numbering of the assembled matrix: bit-exact
+* load-displacement curves: 1e-6 relative, equal Newton iterations per step
+"""
+import numpy as np
+import pytest
+import scipy.sparse as scsp
+import scipy.sparse.linalg as spla
+
+from _golden import ANALYSES, clicks_of, control_of, load, model_of, rel
+
+pytestmark = pytest.mark.gpu
+
+TOL_KERNEL = 1e-10
+TOL_CURVE = 1e-6
+BAND = 1e-8
+
+
+@pytest.fixture(scope="module")
+def fc():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from fcvm_workbench_b200 import fcVM
+    return fcVM
+
+
+def distorted_cube(n=3, seed=0, **kw):
+    from fcvm_workbench_b200.mesh import cube_model
+    m = cube_model(n, size=6.0, mode=kw.pop("mode", "platen"), top_disp=kw.pop("top_disp", 0.05), **kw)
+    rng = np.random.default_rng(seed)
+    m.nocoord = m.nocoord + rng.uniform(-0.05, 0.05, m.nocoord.shape)
+    return m, rng
+
+
+def svm_of(sig):
+    s = sig.reshape(-1, 6).copy()
+    p = s[:, :3].mean(axis=1)
+    s[:, :3] -= p[:, None]
+    return np.sqrt(1.5 * (s[:, :3] ** 2).sum(axis=1) + 3.0 * (s[:, 3:] ** 2).sum(axis=1))
+
+
+# ---- element level ---------------------------------------------------------------------------
+def test_element_stiffness_vs_reference_golden(fc):
+    z = load("kernels")
+    m = model_of(z)
+    with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+        esm = eng.element_matrices()
+    for e in range(m.ne):
+        assert rel(esm[e], z["r_esm"][e]) < TOL_KERNEL, e
+
+
+def test_element_stiffness_vs_oracle_seeded(fc, oracle):
+    m, _ = distorted_cube(4, seed=3)
+    out = oracle.calcGSM(m.elNodes, m.nocoord, m.materialbyElement, {}, 0, 0, 0, m.loadfaces, m.pressure,
+                         m.loadvertices, m.vertexloads, m.loadedges, m.edgeloads, m.loadfaces_uni, m.faceloads,
+                         return_esm=True)
+    with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+        esm = eng.element_matrices()
+    worst = max(rel(esm[e], out[-1][e]) for e in range(m.ne))
+    assert worst < TOL_KERNEL
+    assert np.abs(esm - esm.transpose(0, 2, 1)).max() < 1e-9 * np.abs(esm).max()
+
+
+@pytest.mark.parametrize("tag,LD", [("sm", False), ("ld", True)])
+def test_update_stress_load_vs_reference_golden(fc, tag, LD):
+    z = load("kernels")
+    m = model_of(z)
+    ne, nn = m.ne, m.nn
+    sig_new, sig_test, qin = np.zeros(24 * ne), np.zeros(24 * ne), np.zeros(3 * nn)
+    pgp = np.full(4 * ne, False)
+    fc.update_stress_load(None, m.elNodes, m.nocoord, m.materialbyElement, z[f"{tag}_sy"], z[f"{tag}_disp"],
+                          z[f"{tag}_du"], z[f"{tag}_sig"], sig_new, sig_test, qin, float(z[f"{tag}_Et_E"]), LD, pgp)
+    assert rel(sig_test, z[f"r_{tag}_sig_test"]) < TOL_KERNEL
+    assert rel(sig_new, z[f"r_{tag}_sig_new"]) < TOL_KERNEL
+    assert rel(qin, z[f"r_{tag}_qin"]) < TOL_KERNEL
+    away = np.abs(svm_of(z[f"r_{tag}_sig_test"]) - z[f"{tag}_sy"]) > BAND * z[f"{tag}_sy"]
+    assert away.sum() > 0.9 * away.size
+    assert np.array_equal(pgp[away], z[f"r_{tag}_pgp"][away])
+    assert 0 < pgp.sum() < pgp.size
+
+
+@pytest.mark.parametrize("LD", [False, True])
+def test_update_stress_load_vs_oracle_seeded(fc, oracle, LD):
+    m, rng = distorted_cube(5, seed=11)
+    ne, nn = m.ne, m.nn
+    du = rng.normal(0, 2e-3, 3 * nn)
+    disp = rng.normal(0, 1e-2, 3 * nn)
+    sig = rng.normal(0, 90.0, 24 * ne)
+    sy = 180.0 * (1 + 0.2 * rng.random(4 * ne))
+    o = [np.zeros(24 * ne), np.zeros(24 * ne), np.zeros(3 * nn), np.full(4 * ne, False)]
+    g = [np.zeros(24 * ne), np.zeros(24 * ne), np.zeros(3 * nn), np.full(4 * ne, False)]
+    oracle.update_stress_load(None, m.elNodes, m.nocoord, m.materialbyElement, sy, disp, du, sig, o[0], o[1], o[2],
+                              0.03, LD, o[3])
+    fc.update_stress_load(None, m.elNodes, m.nocoord, m.materialbyElement, sy, disp, du, sig, g[0], g[1], g[2],
+                          0.03, LD, g[3])
+    for a, b in zip(g[:3], o[:3]):
+        assert rel(a, b) < TOL_KERNEL
+    away = np.abs(svm_of(o[1]) - sy) > BAND * sy
+    assert np.array_equal(g[3][away], o[3][away])
+
+
+def test_internal_force_is_bit_reproducible(fc):
+    m, rng = distorted_cube(5, seed=5)
+    du = rng.normal(0, 2e-3, 3 * m.nn)
+    outs = []
+    for _ in range(2):
+        with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+            eng.gp_fill(fc.SIG_YIELD, 150.0)
+            d, q = eng.vec(host=du), eng.vec()
+            eng.update_stress_load(None, d, q, 0.0)
+            outs.append(eng.get(q))
+    assert np.array_equal(outs[0], outs[1])
+
+
+# ---- assembly -----------------------------------------------------------------------------------
+def test_assembled_matrix_pattern_is_bit_exact_and_values_match(fc):
+    z = load("kernels")
+    m = model_of(z)
+    g = z["grav"]
+    ref = scsp.csc_matrix((z["r_stm"], (z["r_row"], z["r_col"])), shape=(3 * m.nn, 3 * m.nn))
+    ref.sum_duplicates()
+    ref.sort_indices()
+    from fcvm_workbench_b200.loads import surface_load_vector
+    with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+        glv = eng.vec(host=surface_load_vector(m.nocoord, m.loadfaces, m.pressure, m.loadvertices, m.vertexloads,
+                                               m.loadedges, m.edgeloads, m.loadfaces_uni, m.faceloads))
+        eng.assemble(glv, tuple(g))
+        indptr, indices, data = eng.export_csc_lower()
+        glv_h, modf = eng.get(glv), eng.get(eng.buf(fc.MODF))
+    assert np.array_equal(indptr, ref.indptr.astype(np.int64))
+    assert np.array_equal(indices, ref.indices.astype(np.int64))
+    assert rel(data, ref.data) < TOL_KERNEL
+    assert rel(glv_h, z["r_glv"]) < TOL_KERNEL
+    assert rel(modf, z["r_modf"]) < TOL_KERNEL
+
+
+@pytest.mark.parametrize("name", ["tensile", "cube2_platen", "cube2_force"])
+def test_calcGSM_dropin_matches_reference_gsm(fc, name):
+    z = load(name)
+    m, c = model_of(z), control_of(z)
+    stm, row, col, glv, modf, V, lsx, lsy, lsz, ne, nn, x = fc.calcGSM(
+        m.elNodes, m.nocoord, m.materialbyElement, m.fix, c.grav_x, c.grav_y, c.grav_z, m.loadfaces, m.pressure,
+        m.loadvertices, m.vertexloads, m.loadedges, m.edgeloads, m.loadfaces_uni, m.faceloads)
+    gsm = scsp.csc_matrix((stm, (row, col)), shape=(3 * nn, 3 * nn))
+    gsm.sort_indices()
+    assert np.array_equal(gsm.indptr, z["r_gsm_indptr"]) and np.array_equal(gsm.indices, z["r_gsm_indices"])
+    assert rel(gsm.data, z["r_gsm_data"]) < TOL_KERNEL
+    assert rel(glv, z["r_glv"]) < TOL_KERNEL and rel(modf, z["r_modf"]) < TOL_KERNEL
+    assert rel(x, z["r_x"]) < 1e-12
+    assert rel([lsx, lsy, lsz], z["r_loadsum"]) < 1e-9 or np.abs(z["r_loadsum"]).max() == 0
+
+
+def test_tangent_assembly_matches_reference_calcTSM(fc):
+    z = load("kernels")
+    m = model_of(z)
+    g = z["grav"]
+    ref = scsp.csc_matrix((z["r_tsm_stm"], (z["r_tsm_row"], z["r_tsm_col"])), shape=(3 * m.nn, 3 * m.nn))
+    ref.sum_duplicates()
+    ref.sort_indices()
+    with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+        eng.gp_put(fc.SIG_OLD, z["ld_sig"])
+        # plastic flags: write through a stress update with the fixture's inputs
+        eng.gp_put(fc.SIG_YIELD, z["ld_sy"])
+        d, u, q = eng.vec(host=z["ld_disp"]), eng.vec(host=z["ld_du"]), eng.vec()
+        eng.update_stress_load(d, u, q, float(z["ld_Et_E"]), LD=True)
+        assert np.array_equal(eng.gp_get(fc.PGP), z["r_ld_pgp"])
+        glv = eng.vec()
+        eng.assemble(glv, tuple(g), tangent=True, disp=d, Et_E=float(z["ld_Et_E"]))
+        indptr, indices, data = eng.export_csc_lower()
+        glv_h, modf = eng.get(glv), eng.get(eng.buf(fc.MODF))
+    assert np.array_equal(indptr, ref.indptr) and np.array_equal(indices, ref.indices)
+    assert rel(data, ref.data) < 1e-9
+    assert rel(glv_h, z["r_tsm_glv"]) < TOL_KERNEL and rel(modf, z["r_tsm_modf"]) < 1e-9
+
+
+# ---- linear solve ---------------------------------------------------------------------------------
+def test_spmv_and_pcg_vs_direct_solver(fc):
+    m, rng = distorted_cube(5, seed=7)
+    with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+        glv = eng.vec()
+        eng.assemble(glv, (0.0, 0.0, -9.81))
+        indptr, indices, data = eng.export_csc_lower()
+        n = eng.ndof
+        low = scsp.csc_matrix((data, indices, indptr), shape=(n, n))
+        K = (low + scsp.tril(low, k=-1).T).tocsc()
+        xh = rng.normal(size=n)
+        x, y = eng.vec(host=xh), eng.vec()
+        eng.spmv(x, y)
+        assert rel(eng.get(y), K @ xh) < 1e-12
+        b = rng.normal(size=n)
+        bd, sol = eng.vec(host=b), eng.vec()
+        its, rr = eng.solve(bd, sol, rtol=1e-12)
+        ref = spla.splu(K).solve(b)
+        assert rr <= 1e-12 and 0 < its < 5000
+        assert rel(eng.get(sol), ref) < 1e-8
+        # bit-reproducible
+        sol2 = eng.vec()
+        its2, _ = eng.solve(bd, sol2, rtol=1e-12)
+        assert its2 == its and np.array_equal(eng.get(sol), eng.get(sol2))
+        # host drop-in: x = factor(b)
+        assert rel(eng.host_solve(b, rtol=1e-12), ref) < 1e-8
+
+
+# ---- Gauss-point post-processing -------------------------------------------------------------------
+def test_peeq_csr_and_nodal_mapping_vs_reference_golden(fc):
+    z = load("kernels")
+    m = model_of(z)
+    with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+        sy, peeq, csr = z["sm_sy"].copy(), z["pq_peeq0"].copy(), z["pq_csr0"].copy()
+        triax, pres, svm, ecr = (np.zeros(4 * m.ne) for _ in range(4))
+        res = fc.update_PEEQ_CSR(m.ne, m.materialbyElement, z["r_sm_sig_test"], z["r_sm_sig_new"], sy,
+                                 float(z["pq_ult"]), peeq, csr, triax, pres, svm, ecr, float(z["sm_Et_E"]),
+                                 engine=eng)
+        for a, k in ((sy, "sy"), (peeq, "peeq"), (csr, "csr"), (triax, "triax"), (pres, "pressure"),
+                     (svm, "sigmises"), (ecr, "ecr")):
+            assert rel(a, z["r_pq_" + k]) < TOL_KERNEL, k
+        gp = int(np.argmax(z["r_pq_csr"]))
+        assert res[0] == gp and res[1] == pytest.approx(z["r_pq_csr"][gp], rel=1e-12)
+        assert res[7] == pytest.approx(z["r_pq_peeq"].max(), rel=1e-12)
+    for averaged, k in ((False, "max"), (True, "avg")):
+        t = fc.mapStresses(averaged, m.elNodes, m.nocoord, z["r_sm_sig_new"], z["r_pq_peeq"], z["r_pq_sigmises"],
+                           z["r_pq_csr"], m.noce, 180.0)
+        for a, f in zip(t, ("stress", "peeq", "csr", "svm", "triax")):
+            assert rel(a, z[f"r_map_{k}_{f}"]) < TOL_KERNEL, (k, f)
+
+
+# ---- whole analyses -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ANALYSES)
+def test_load_displacement_curve_vs_reference_golden(fc, name):
+    z = load(name)
+    m, c = model_of(z), control_of(z)
+    o = fc.calcDisp(m, c, clicks=clicks_of(z), rtol=1e-11)
+    assert list(o["iters"]) == list(z["r_iters"]), "Newton iterations per step differ from the reference"
+    for k in ("lout", "un", "peeqplot", "pplot", "svmplot", "triaxplot", "ecrplot", "csrplot"):
+        assert rel(o[k], z["r_" + k]) < TOL_CURVE, k
+    for k in ("displacements", "disp_el", "stresses", "peeq", "sigmises", "csr"):
+        assert rel(o[k], z["r_" + k]) < 1e-5, k
+    if name == "tensile":
+        assert np.array_equal(o["crip"], z["r_crip"])
+        assert [float(f"{v:.2e}") for v in o["x_crip"][-1]] == [9.31, 7.24, 9.31]     # tensile.out, last rows
+
+
+def test_collapse_analysis_vs_oracle_larger_mesh(fc, oracle):
+    from fcvm_workbench_b200.control import Control
+    from fcvm_workbench_b200.mesh import cube_model
+    m = cube_model(4, mode="punch", top_disp=0.12, nxyz=(5, 4, 4))
+    c = Control(sig_yield=200.0, nstep=6, error_max=1e-5, target_LF=2.0, Et_E=0.0)
+    ref = oracle.calcDisp(m, c)
+    o = fc.calcDisp(m, c, rtol=1e-11)
+    assert list(o["iters"]) == list(ref["iters"])
+    assert rel(o["lout"], ref["lout"]) < TOL_CURVE and rel(o["un"], ref["un"]) < TOL_CURVE
+    assert rel(o["peeqplot"], ref["peeqplot"]) < TOL_CURVE
+    away = np.abs(svm_of(ref["sig_test"]) - ref["sig_yield"]) > BAND * ref["sig_yield"]
+    assert np.array_equal(o["pgp"][away], ref["pgp"][away])
+    assert 0 < o["pgp"].sum() < o["pgp"].size
+
+
+def test_size_independent_properties_at_scale(fc):
+    """At a size the oracle would take minutes for: symmetry of the operator, equilibrium of the
+    internal force vector (sum of nodal forces of a self-equilibrated stress field is zero) and
+    the elastic patch test (uniform strain -> uniform stress, no plastic points)."""
+    from fcvm_workbench_b200.mesh import cube_model
+    m = cube_model(16, size=10.0, mode="platen", top_disp=0.01)
+    rng = np.random.default_rng(2)
+    with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+        glv = eng.vec()
+        eng.assemble(glv)
+        n = eng.ndof
+        xh, yh = rng.normal(size=n), rng.normal(size=n)
+        x, y, kx, ky = eng.vec(host=xh), eng.vec(host=yh), eng.vec(), eng.vec()
+        eng.spmv(x, kx)
+        eng.spmv(y, ky)
+        a, b = eng.dot(y, kx), eng.dot(x, ky)
+        assert abs(a - b) < 1e-10 * max(abs(a), abs(b))
+        # patch test: u = eps * (x, -nu x ... ) linear field -> constant stress E*eps in z
+        eps = 1e-4
+        nu, E = m.materialbyElement[0][1], m.materialbyElement[0][0]
+        u = np.zeros((m.nn, 3))
+        u[:, 2] = eps * m.nocoord[:, 2]
+        u[:, 0] = -nu * eps * m.nocoord[:, 0]
+        u[:, 1] = -nu * eps * m.nocoord[:, 1]
+        eng.gp_fill(fc.SIG_YIELD, 1e9)
+        du, q = eng.vec(host=u.ravel()), eng.vec()
+        eng.update_stress_load(None, du, q, 0.0)
+        sig = eng.gp_get(fc.SIG_NEW).reshape(-1, 6)
+        assert np.abs(sig[:, 2] - E * eps).max() < 1e-9 * E * eps + 1e-9
+        assert np.abs(np.delete(sig, 2, axis=1)).max() < 1e-9 * E * eps + 1e-9
+        assert eng.plastic_count() == 0
+        qh = eng.get(q).reshape(-1, 3)
+        assert np.abs(qh.sum(axis=0)).max() < 1e-8 * np.abs(qh).sum()
+        interior = np.all((m.nocoord > 1e-9) & (m.nocoord < 10.0 - 1e-9), axis=1)
+        assert np.abs(qh[interior]).max() < 1e-8 * np.abs(qh).max()

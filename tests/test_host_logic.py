@@ -1,0 +1,95 @@
+"""Host-side logic that needs no GPU: control files, model readers, meshes, load vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from fcvm_workbench_b200.control import Control, read_control
+from fcvm_workbench_b200.loads import surface_load_vector
+from fcvm_workbench_b200.mesh import box_mesh, cube_model
+from fcvm_workbench_b200.model import Model
+
+from _golden import load, model_of
+
+
+def test_control_roundtrip(tmp_path):
+    c = Control(sig_yield=355.0, nstep=7, gnl="GNLY", disp_output="incremental")
+    p = tmp_path / "x.inp"
+    c.write(str(p))
+    assert read_control(str(p)) == c
+
+
+def test_control_short_file_gets_reference_defaults(tmp_path):
+    p = tmp_path / "old.inp"
+    p.write_text("\n".join(["100", "0.0", "0.0", "0.0", "25", "20", "0.001", "1.2", "2.0", "1.2", "1.2",
+                            "incremental", "0.25", "0.0", "3", "PEEQ", "unaveraged"]) + "\n\n")
+    c = read_control(str(p))
+    assert c.nstep == 25 and c.gnl == "GNLN" and c.target_LF == 3.0
+
+
+def test_control_missing_field_is_an_error(tmp_path):
+    p = tmp_path / "bad.inp"
+    p.write_text("100\n0.0\n")
+    with pytest.raises(ValueError):
+        read_control(str(p))
+
+
+@pytest.mark.parametrize("n", [(1, 1, 1), (3, 2, 4)])
+def test_box_mesh_is_conforming_and_positive(n):
+    el, xyz = box_mesh(*n, 3.0, 2.0, 4.0)
+    assert el.shape == (6 * n[0] * n[1] * n[2], 10)
+    assert xyz.shape[0] == (2 * n[0] + 1) * (2 * n[1] + 1) * (2 * n[2] + 1)
+    assert len(np.unique(el)) == xyz.shape[0] and el.min() == 1
+    X = xyz[el - 1]
+    pairs = {4: (0, 1), 5: (1, 2), 6: (0, 2), 7: (0, 3), 8: (1, 3), 9: (2, 3)}
+    for k, (a, b) in pairs.items():
+        assert np.allclose(X[:, k], 0.5 * (X[:, a] + X[:, b]))
+    vol = np.einsum("ei,ei->e", np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), X[:, 3] - X[:, 0]) / 6
+    assert (vol > 0).all() and vol.sum() == pytest.approx(24.0)
+
+
+def test_model_npz_roundtrip(tmp_path):
+    m = cube_model(2, mode="force", top_disp=10.0)
+    p = str(tmp_path / "m.npz")
+    m.save_npz(p)
+    r = Model.load_npz(p)
+    assert np.array_equal(r.elNodes, m.elNodes) and r.fix == m.fix and np.array_equal(r.loadfaces_uni, m.loadfaces_uni)
+
+
+def test_surface_loads_match_reference_glv():
+    """glv of the reference's calcGSM for the tensile model (Face6 force) and the force cube."""
+    for name in ("tensile", "cube2_force"):
+        z = load(name)
+        m = model_of(z)
+        if float(z["c_grav_z"]) != 0.0:
+            continue                       # gravity part is integrated on the device
+        glv = surface_load_vector(m.nocoord, m.loadfaces, m.pressure, m.loadvertices, m.vertexloads, m.loadedges,
+                                  m.edgeloads, m.loadfaces_uni, m.faceloads)
+        assert np.abs(glv - z["r_glv"]).max() < 1e-9 * np.abs(z["r_glv"]).max()
+
+
+def test_surface_loads_all_kinds_vs_oracle(oracle):
+    m = cube_model(2, mode="force", top_disp=300.0)
+    rng = np.random.default_rng(1)
+    xyz = m.nocoord + rng.uniform(-.05, .05, m.nocoord.shape)
+    lf = np.vstack([m.loadfaces, m.loadfaces_uni[1:4]])
+    pr = np.array([0., 3., -2., 5.])
+    le = np.array([[0, 0, 0], [1, 3, 2], [3, 5, 4]])
+    el = np.array([[0, 0, 0], [1., 2, 3], [4, 5, 6.]])
+    lv = np.array([[0], [7], [9]])
+    vl = np.array([[0, 0, 0], [1., 0, 2], [0, 3, 1.]])
+    for disp in (None, rng.normal(0, .01, 3 * m.nn)):
+        a = surface_load_vector(xyz, lf, pr, lv, vl, le, el, m.loadfaces_uni, m.faceloads, disp=disp)
+        b = oracle.load_vector(xyz, lf, pr, lv, vl, le, el, m.loadfaces_uni, m.faceloads, disp=disp)
+        assert np.abs(a - b).max() < 1e-12 * np.abs(b).max()
+
+
+def test_fcstd_reader_on_reference_model():
+    path = "/root/reference/freeCAD files/tensile.FCStd"
+    if not os.path.isfile(path):
+        pytest.skip("reference models not present on this machine")
+    from fcvm_workbench_b200.fcstd import read_fcstd
+    m = read_fcstd(path)
+    z = load("tensile")
+    assert np.array_equal(m.elNodes, z["m_elNodes"]) and np.allclose(m.nocoord, z["m_nocoord"])
+    assert sorted(m.fix) == sorted(int(d) for d in z["m_fix_dof"])
