@@ -199,8 +199,9 @@ k_coo_reduce(int64_t nslices, const int32_t *__restrict__ slice_ptr, const uint3
 // node -- the sum of the 1.0 entries the reference emits per element (fcVM.py:773-777)
 __global__ void __launch_bounds__(SELL_C)
 k_apply_constraints(int64_t nslices, const int32_t *__restrict__ slice_ptr, const int32_t *__restrict__ slot_node,
-                    const int32_t *__restrict__ colidx, const uint8_t *__restrict__ fixmask,
-                    const int32_t *__restrict__ n2e_ptr, double *__restrict__ vals) {
+                    const int32_t *__restrict__ colidx, const int32_t *__restrict__ diag_pos,
+                    const uint8_t *__restrict__ fixmask, const int32_t *__restrict__ n2e_ptr,
+                    double *__restrict__ vals) {
   const int64_t s = blockIdx.x;
   const int lane = threadIdx.x;
   const int32_t row = slot_node[s * SELL_C + lane];
@@ -208,6 +209,7 @@ k_apply_constraints(int64_t nslices, const int32_t *__restrict__ slice_ptr, cons
   const bool fr[3] = {fixmask[3 * (int64_t)row] != 0, fixmask[3 * (int64_t)row + 1] != 0,
                       fixmask[3 * (int64_t)row + 2] != 0};
   const double cnt = (double)(n2e_ptr[row + 1] - n2e_ptr[row]);
+  const int64_t dpos = diag_pos[row];       // padding entries also carry col == row: only this one is the diagonal
   for (int32_t k = slice_ptr[s]; k < slice_ptr[s + 1]; k++) {
     const int64_t pos = (int64_t)k * SELL_C + lane;
     const int32_t col = colidx[pos];
@@ -219,7 +221,7 @@ k_apply_constraints(int64_t nslices, const int32_t *__restrict__ slice_ptr, cons
     for (int i = 0; i < 3; i++)
 #pragma unroll
       for (int j = 0; j < 3; j++)
-        if (fr[i] || fc[j]) o[(3 * i + j) * SELL_C] = (row == col && i == j) ? cnt : 0.0;
+        if (fr[i] || fc[j]) o[(3 * i + j) * SELL_C] = (pos == dpos && i == j) ? cnt : 0.0;
   }
 }
 
@@ -368,7 +370,8 @@ extern "C" int fcvm_assemble(fcvm_ctx *c, int tangent, const double *disp, doubl
   FCVM_TRY(launch_spmv(c, c->fixval, c->pcg_q));
   FCVM_TRY(fcvm_interface_sum(c, c->pcg_q));
   k_apply_constraints<<<(unsigned)c->nslices, SELL_C, 0, c->stream>>>(c->nslices, c->slice_ptr, c->slot_node,
-                                                                     c->colidx, c->fixmask, c->n2e_ptr, c->vals);
+                                                                     c->colidx, c->diag_pos, c->fixmask, c->n2e_ptr,
+                                                                     c->vals);
   if (!c->diag9) FCVM_CUDA(cudaMalloc((void **)&c->diag9, sizeof(double) * 9 * c->nn));
   k_extract_diag<<<grid_for(c->nn, 128), 128, 0, c->stream>>>(c->nn, c->diag_pos, c->vals, c->diag9);
   for (int i = 0; i < 3; i++) FCVM_TRY(fcvm_interface_sum(c, c->diag9 + (int64_t)i * 3 * c->nn));
