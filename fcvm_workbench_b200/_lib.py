@@ -75,6 +75,7 @@ _SIGNATURES = {
     "fcvm_profile_enable": [ctxp, c_int],
     "fcvm_profile_get": [ctxp, c_int, f64p, i64p],
     "fcvm_profile_reset": [ctxp],
+    "fcvm_profile_seen": [ctxp, c_int],
     "fcvm_matrix_stats": [ctxp, i64p, i64p, i64p],
     "fcvm_last_error": [],
     "fcvm_version": [],
@@ -83,8 +84,9 @@ _SIGNATURES = {
     "fcvm_launch_count": [ctxp],
 }
 _RESTYPE = {"fcvm_last_error": c_char_p, "fcvm_num_elements": c_int64, "fcvm_num_nodes": c_int64,
-            "fcvm_launch_count": c_int64}
-_NO_CHECK = {"fcvm_last_error", "fcvm_version", "fcvm_num_elements", "fcvm_num_nodes", "fcvm_launch_count"}
+            "fcvm_launch_count": c_int64, "fcvm_profile_seen": c_int64}
+_NO_CHECK = {"fcvm_last_error", "fcvm_version", "fcvm_num_elements", "fcvm_num_nodes", "fcvm_launch_count",
+             "fcvm_profile_seen"}
 
 _cdll = None
 

@@ -50,8 +50,17 @@ constexpr double GP_B = 0.585410196624968;
 constexpr double GP_W = 0.041666666666667;
 
 struct Profile {
-  double ms[NUM_PROFILE];
-  int64_t launches[NUM_PROFILE];
+  double ms[NUM_PROFILE];        // summed duration of the timed launches
+  int64_t launches[NUM_PROFILE]; // launches that were timed
+  int64_t seen[NUM_PROFILE];     // all launches since the reset
+};
+
+// asynchronous sampling: event pairs recorded around every stride-th launch of a family,
+// resolved (one synchronisation) when the profile is read -- the timed region is not disturbed
+constexpr int PROF_POOL = 4096;
+struct ProfSample {
+  int which;
+  cudaEvent_t e0, e1;
 };
 
 }  // namespace fcvm
@@ -62,8 +71,11 @@ struct fcvm_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // fcvm_timer_*
   cudaEvent_t pev0 = nullptr, pev1 = nullptr;    // profiling
-  int profiling = 0;
+  int profiling = 0;             // 0 off, 1 every launch (synchronous), 2 sampled (asynchronous)
+  int prof_stride = 8;
   fcvm::Profile prof{};
+  std::vector<fcvm::ProfSample> prof_pool;
+  size_t prof_used = 0;
   int64_t launches = 0;
 
   // mesh
@@ -135,21 +147,32 @@ namespace fcvm {
 
 inline int grid_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
-// profiling wrapper: records events around a launch when enabled
+// profiling wrapper: CUDA events on the launching stream around one launch
 struct ProfScope {
   fcvm_ctx *c;
   int which;
+  fcvm::ProfSample *smp = nullptr;
   ProfScope(fcvm_ctx *ctx, int w) : c(ctx), which(w) {
-    if (c->profiling) cudaEventRecord(c->pev0, c->stream);
+    if (!c->profiling) return;
+    const int64_t k = c->prof.seen[which]++;
+    if (c->profiling == 1) {
+      cudaEventRecord(c->pev0, c->stream);
+    } else if ((k % c->prof_stride) == 0 && c->prof_used < c->prof_pool.size()) {
+      smp = &c->prof_pool[c->prof_used++];
+      smp->which = which;
+      cudaEventRecord(smp->e0, c->stream);
+    }
   }
   ~ProfScope() {
-    if (c->profiling) {
+    if (c->profiling == 1) {
       cudaEventRecord(c->pev1, c->stream);
       cudaEventSynchronize(c->pev1);
       float ms = 0.f;
       cudaEventElapsedTime(&ms, c->pev0, c->pev1);
       c->prof.ms[which] += ms;
       c->prof.launches[which] += 1;
+    } else if (smp) {
+      cudaEventRecord(smp->e1, c->stream);
     }
   }
 };

@@ -334,6 +334,7 @@ extern "C" int fcvm_destroy(fcvm_ctx *c) {
   if (c->h_arg) cudaFreeHost(c->h_arg);
   if (c->stage) cudaFreeHost(c->stage);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->pev0); cudaEventDestroy(c->pev1);
+  for (auto &s : c->prof_pool) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
   cudaStreamDestroy(c->own_stream);
   delete c;
   return FCVM_OK;
@@ -819,14 +820,38 @@ extern "C" int fcvm_timer_stop_ms(fcvm_ctx *c, float *ms) {
   return FCVM_OK;
 }
 
+static int resolve_samples(fcvm_ctx *c) {
+  if (c->prof_used == 0) return FCVM_OK;
+  FCVM_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < c->prof_used; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->prof_pool[i].e0, c->prof_pool[i].e1) == cudaSuccess) {
+      c->prof.ms[c->prof_pool[i].which] += ms;
+      c->prof.launches[c->prof_pool[i].which] += 1;
+    }
+  }
+  c->prof_used = 0;
+  return FCVM_OK;
+}
+
 extern "C" int fcvm_profile_enable(fcvm_ctx *c, int on) {
-  FCVM_CHECK(c, FCVM_E_ARG, "null context");
-  c->profiling = on;
+  FCVM_CHECK(c && on >= 0, FCVM_E_ARG, "fcvm_profile_enable: bad argument");
+  FCVM_TRY(resolve_samples(c));
+  if (on >= 2 && c->prof_pool.empty()) {
+    c->prof_pool.resize(PROF_POOL);
+    for (auto &s : c->prof_pool) {
+      FCVM_CUDA(cudaEventCreate(&s.e0));
+      FCVM_CUDA(cudaEventCreate(&s.e1));
+    }
+  }
+  c->profiling = on >= 2 ? 2 : on;
+  if (on >= 2) c->prof_stride = on;      // on = stride of the sampled mode (>= 2)
   return FCVM_OK;
 }
 
 extern "C" int fcvm_profile_get(fcvm_ctx *c, int which, double *ms, int64_t *launches) {
   FCVM_CHECK(c && which >= 0 && which < NUM_PROFILE, FCVM_E_ARG, "fcvm_profile_get: bad index");
+  FCVM_TRY(resolve_samples(c));
   if (ms) *ms = c->prof.ms[which];
   if (launches) *launches = c->prof.launches[which];
   return FCVM_OK;
@@ -834,8 +859,13 @@ extern "C" int fcvm_profile_get(fcvm_ctx *c, int which, double *ms, int64_t *lau
 
 extern "C" int fcvm_profile_reset(fcvm_ctx *c) {
   FCVM_CHECK(c, FCVM_E_ARG, "null context");
+  FCVM_TRY(resolve_samples(c));
   memset(&c->prof, 0, sizeof(c->prof));
   return FCVM_OK;
+}
+
+extern "C" int64_t fcvm_profile_seen(fcvm_ctx *c, int which) {
+  return (c && which >= 0 && which < NUM_PROFILE) ? c->prof.seen[which] : 0;
 }
 
 extern "C" int fcvm_matrix_stats(fcvm_ctx *c, int64_t *stored, int64_t *real, int64_t *bytes) {

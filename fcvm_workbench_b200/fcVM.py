@@ -294,18 +294,20 @@ class Engine:
         call("fcvm_timer_stop_ms", self._ctx, ctypes.byref(ms))
         return ms.value
 
-    def profile(self, on: bool):
-        call("fcvm_profile_enable", self._ctx, 1 if on else 0)
+    def profile(self, on):
+        """0/False off, 1/True every launch (synchronous), k >= 2 every k-th launch (asynchronous)."""
+        call("fcvm_profile_enable", self._ctx, int(on))
         call("fcvm_profile_reset", self._ctx)
 
     def profile_get(self):
+        """family -> (summed ms of timed launches, timed launches, all launches)."""
         names = ("spmv", "stress_update", "node_gather", "pcg_vector", "assembly")
         out = {}
         for i, k in enumerate(names):
             ms = ctypes.c_double()
             n = ctypes.c_int64()
             call("fcvm_profile_get", self._ctx, i, ctypes.byref(ms), ctypes.byref(n))
-            out[k] = (ms.value, n.value)
+            out[k] = (ms.value, n.value, int(call("fcvm_profile_seen", self._ctx, i)))
         return out
 
     def launch_count(self) -> int:
@@ -577,7 +579,8 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
                 error = rnorm / qnorm
                 say(f"Iteration: {iterat}, Error: {error:.2e}")
                 if on_iteration is not None:
-                    on_iteration(step, iterat, error)
+                    on_iteration(dict(eng=eng, step=step, iterat=iterat, iterat_tot=iterat_tot, error=error,
+                                      pcg_iterations=its, lbd=lbd))
                 if iterat > iterat_max:                                   # fcVM.py:1457-1484
                     say(f"RESTART # {restart + 1}")
                     if restart > 3:

@@ -179,12 +179,17 @@ int fcvm_host_solve(fcvm_ctx *ctx, const double *b, double *x, double rtol, int 
 /* ---- timing helpers (CUDA events on the context's stream) ---------------------------------- */
 int fcvm_timer_start(fcvm_ctx *ctx);
 int fcvm_timer_stop_ms(fcvm_ctx *ctx, float *ms);
-/* accumulated device time and launch counts per kernel family since the last reset;
+/* Device time per kernel family, measured with CUDA events on the launching stream;
  * which: 0 = spmv, 1 = stress update, 2 = node gather, 3 = pcg vector kernels, 4 = assembly.
- * Only collected while profiling is enabled (adds two event records per launch). */
+ * on = 0 off; 1 = every launch, synchronising after each (exact, slows the run);
+ * on >= 2 = every on-th launch of a family, asynchronously (event pairs from a pool, resolved
+ * when read): the timed region keeps running undisturbed.
+ * fcvm_profile_get returns the summed duration and the number of launches that were timed;
+ * fcvm_profile_seen the number of all launches of the family since the reset. */
 int fcvm_profile_enable(fcvm_ctx *ctx, int on);
 int fcvm_profile_get(fcvm_ctx *ctx, int which, double *ms, int64_t *launches);
 int fcvm_profile_reset(fcvm_ctx *ctx);
+int64_t fcvm_profile_seen(fcvm_ctx *ctx, int which);
 int64_t fcvm_launch_count(fcvm_ctx *ctx);
 
 /* Matrix storage facts for roofline arithmetic: stored 3x3 blocks (incl. padding) and real blocks. */
