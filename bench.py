@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Throughput of the fcVM Newton / load-stepping hot path on B200 (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA through the C ABI)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+Workload (``config.workload``): synthetic structured C3D10 cube, ``6 n^3`` elements (n = 55:
+998,250 elements, 1,367,631 nodes), clamped bottom, rough rigid platen pushed into the top
+face, elastic-perfectly-plastic von Mises material, displacement-controlled load sweep
+(fcVM.py:1304-1559 semantics).  A *step* is one Newton iteration of that sweep: one linear
+solve with the elastic stiffness (PCG on the device instead of CHOLMOD's ``factor(f)``), the
+arc-length update, the radial-return stress update at every Gauss point with the internal-force
+assembly, and the residual norm -- plus the per-load-step bookkeeping that falls between two
+iterations (update_PEEQ_CSR, state roll-over).  Warm-up iterations are the first W Newton
+iterations of the sweep (the elastic first load step needs none and is passed before).
+
+``value`` = Gauss points x Newton iterations / second with every array resident in HBM
+(``newton_iters_per_s`` and the raw stress-update rate are given beside it); ``e2e`` is the same
+sweep driven through the HOST-buffer C ABI (hostpath.HostEngine: numpy arrays in page-locked
+memory, every heavy call pays its PCIe copies).  The matrix (2.95 GB) and the Gauss-point state
+(0.6 GB) are far larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
+
+For N > 1 (torchrun) the same 1M-element mesh is partitioned element-wise into N slabs (strong
+scaling); shared-node sums and PCG dot products go through NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "newton_gauss_point_updates_per_s"
+UNIT = "GP-updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--n", type=int, default=55, help="cells per cube edge (elements = 6 n^3)")
+    ap.add_argument("--rtol", type=float, default=1e-8, help="PCG relative residual per linear solve")
+    ap.add_argument("--cpu-n", type=int, default=12, help="cube edge of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def workload(n):
+    from fcvm_workbench_b200.control import Control
+    from fcvm_workbench_b200.mesh import cube_model
+    m = cube_model(n, size=10.0, mode="platen", top_disp=0.05)
+    c = Control(sig_yield=240.0, nstep=10, iterat_max=20, error_max=1e-3, relax=1.2, target_LF=1.0, Et_E=0.0)
+    return m, c
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not (t0 - 0.1 <= t <= t1 + 0.3):
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class Sweep:
+    """Drives calcDisp and times Newton iterations W+1 .. W+K with CUDA events on the engine's stream."""
+
+    def __init__(self, eng, W, K, barrier=None, profile_stride=0):
+        self.eng, self.W, self.K, self.barrier, self.stride = eng, W, K, barrier, profile_stride
+        self.ms = None
+        self.t0 = self.t1 = None
+        self.launch0 = self.launch1 = 0
+        self.pcg_its = []
+        self.bytes0 = (0, 0)
+        self.prof = None
+
+    def _sync(self):
+        self.eng.synchronize()
+        if self.barrier is not None:
+            self.barrier()
+            self.eng.synchronize()
+
+    def hook(self, d):
+        from fcvm_workbench_b200.fcVM import StopAnalysis
+        it = d["iterat_tot"]
+        dev = getattr(self.eng, "dev", self.eng)
+        if it == self.W:
+            self._sync()
+            if self.stride:
+                dev.profile(self.stride)
+            self.bytes0 = (getattr(self.eng, "h2d_bytes", 0), getattr(self.eng, "d2h_bytes", 0))
+            self.launch0 = dev.launch_count()
+            self.t0 = time.time()
+            dev.timer_start()
+        elif it > self.W:
+            self.pcg_its.append(d["pcg_iterations"])
+        if it == self.W + self.K:
+            self._sync()
+            self.ms = dev.timer_stop_ms()
+            self.t1 = time.time()
+            self.launch1 = dev.launch_count()
+            self.bytes1 = (getattr(self.eng, "h2d_bytes", 0), getattr(self.eng, "d2h_bytes", 0))
+            if self.stride:
+                self.prof = dev.profile_get()
+                dev.profile(0)
+            raise StopAnalysis()
+
+
+def run_sweep(model, ctl, eng, W, K, rtol, barrier=None, profile_stride=0):
+    from fcvm_workbench_b200 import fcVM
+    sw = Sweep(eng, W, K, barrier, profile_stride)
+    # W = 0: the hook of iteration 0 does not exist; start the clock on the first call instead
+    if W == 0:
+        raise SystemExit("--warmup must be >= 1 (the contract asks for >= 3)")
+    out = fcVM.calcDisp(model, ctl, engine=eng, rtol=rtol, max_iter=200000, on_iteration=sw.hook)
+    if sw.ms is None:
+        raise SystemExit(f"the load sweep ended after {out['iterat_tot']} Newton iterations, fewer than "
+                         f"warmup+steps = {W + K}: lower --steps or raise the load")
+    return sw, out
+
+
+def kernel_report(eng, model, prof, hbm_peak):
+    """Algorithmic bytes per launch of each kernel family ('Kernels and their rooflines')."""
+    st = eng.matrix_stats()
+    ne, nn = eng.ne, eng.nn
+    alg = {
+        # real 3x3 blocks (72 B) + their column index (4 B) + x read + y written once
+        "spmv": st["blocks_real"] * 76 + 2 * 24 * nn,
+        # conn 40 B, sig_old 192 B + sig_yield 32 B read, sig_new + sig_test 384 B + pgp 4 B written,
+        # nodal xyz + du read once (48 B per node), element force vector written (240 B)
+        "stress_update": ne * (40 + 192 + 32 + 384 + 4 + 240) + nn * 48,
+        # element force vectors read (240 B), node->element list (40 B), qin written (24 B per node)
+        "node_gather": ne * (240 + 40) + nn * 24,
+    }
+    rep = {}
+    for k, (ms, timed, seen) in prof.items():
+        if timed == 0:
+            continue
+        avg = ms / timed
+        r = {"avg_ms": round(avg, 5), "timed_launches": timed, "launches": seen}
+        if k in alg:
+            gbs = alg[k] / avg / 1e6
+            r.update(algorithmic_bytes=int(alg[k]), achieved_gbs=round(gbs, 1), frac_of_hbm_peak=round(gbs / hbm_peak, 4))
+        rep[k] = r
+    return rep, alg
+
+
+def cpu_baseline(W, K, n):
+    """The oracle (CPU port of the reference routines + a direct sparse solve standing in for CHOLMOD)
+    on a bounded sample of the same workload, timed on this box's host cores."""
+    from oracle import fcvm_oracle as orc
+    m, c = workload(n)
+    stamps = []
+
+    def hook(d):
+        stamps.append(time.perf_counter())
+        if d["iterat_tot"] == W + K:
+            raise orc.StopAnalysis()
+
+    t_setup = time.perf_counter()
+    try:
+        orc.calcDisp(m, c, on_iteration=hook)
+    except orc.StopAnalysis:
+        pass
+    if len(stamps) < W + K:
+        raise SystemExit("cpu sample ended before warmup+steps Newton iterations")
+    dt = stamps[W + K - 1] - stamps[W - 1]
+    return {"value": 4 * m.ne * K / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"cube n={n}: {m.ne} elements, {K} Newton iterations after {W} warm-up; modified Newton with "
+                      f"one SuperLU factorisation (CHOLMOD stand-in, {stamps[0] - t_setup:.1f} s, untimed) and "
+                      f"the C restatement of the numba element routines",
+            "newton_iters_per_s": K / dt, "ms_per_step": 1e3 * dt / K, "elements": m.ne}
+
+
+def main():
+    a = parse()
+    rank, world, local = dist_env()
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cb = cpu_baseline(a.warmup, a.steps, a.cpu_n)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"structured C3D10 cube, von Mises platen load sweep; bounded CPU sample "
+                                       f"n={a.cpu_n} ({cb['elements']} elements) of the n={a.n} workload"},
+                "newton_iters_per_s": cb["newton_iters_per_s"], "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    from fcvm_workbench_b200 import fcVM
+    from fcvm_workbench_b200.hostpath import HostEngine
+    torch.cuda.set_device(local)
+    barrier = None
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        from fcvm_workbench_b200 import partition
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        tok = torch.zeros(1, device="cuda")
+
+        def barrier():
+            dist.all_reduce(tok)
+            torch.cuda.synchronize()
+
+    hbm_peak, peak_src = peaks()
+    t_mesh = time.time()
+    gmodel, ctl = workload(a.n)
+    ne_total = gmodel.ne
+    if world > 1:
+        part = partition.slab_partition(gmodel, world)
+        model = part.local_model(rank)
+        comm = partition.Comm(part, rank, world)
+    else:
+        model = gmodel
+    t_mesh = time.time() - t_mesh
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    eng = fcVM.Engine(model.elNodes, model.nocoord, model.materialbyElement, model.fix, device=local, comm=comm)
+    sw, out = run_sweep(model, ctl, eng, a.warmup, a.steps, a.rtol, barrier, profile_stride=32)
+    ms = sw.ms
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clk = clocks.stop(sw.t0, sw.t1) if rank == 0 else None
+    kern, alg = kernel_report(eng, model, sw.prof, hbm_peak)
+    launches = sw.launch1 - sw.launch0
+    # raw Gauss-point update rate of the stress-update kernel + its deterministic force assembly
+    gp_rate = None
+    if "stress_update" in kern:
+        t_su = kern["stress_update"]["avg_ms"] + kern.get("node_gather", {"avg_ms": 0.0})["avg_ms"]
+        gp_rate = 4 * ne_total / (t_su * 1e-3) if world == 1 else 4 * model.ne * world / (t_su * 1e-3)
+    eng.close()
+
+    e2e = None
+    if not a.no_e2e and world == 1:
+        heng = HostEngine(model.elNodes, model.nocoord, model.materialbyElement, model.fix, device=local)
+        hs, _ = run_sweep(model, ctl, heng, a.warmup, a.steps, a.rtol)
+        e2e = {"value": 4 * ne_total * a.steps / (hs.ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int((hs.bytes1[0] - hs.bytes0[0]) / a.steps),
+               "d2h_bytes_per_step": int((hs.bytes1[1] - hs.bytes0[1]) / a.steps),
+               "ms_per_step": hs.ms / a.steps, "newton_iters_per_s": a.steps / (hs.ms * 1e-3),
+               "path": "hostpath.HostEngine: fcvm_host_solve + fcvm_host_update_stress_load on page-locked numpy arrays"}
+        heng.close()
+    elif world > 1:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "host-buffer path is measured at N=1"}
+
+    cb = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cb = cpu_baseline(min(a.warmup, 3), min(a.steps, 10), a.cpu_n)
+
+    if rank == 0:
+        spmv = kern.get("spmv", {})
+        line = {
+            "metric": METRIC, "value": 4 * ne_total * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"structured C3D10 cube n={a.n}: {ne_total} elements, {gmodel.nn} nodes, von Mises "
+                                   "(elastic-perfectly-plastic) platen compression, displacement-controlled load sweep",
+                       "elements": ne_total, "nodes": gmodel.nn, "step": "one Newton iteration (PCG solve + arc-length "
+                       "update + radial-return stress update + internal force + residual)",
+                       "pcg_rtol": a.rtol, "partition": f"{world} element slab(s)",
+                       "l2": "inputs exceed L2 (matrix 2.95 GB, Gauss-point state 0.6 GB vs 126 MB)"},
+            "newton_iters_per_s": a.steps / (ms * 1e-3),
+            "stress_update_gauss_points_per_s": gp_rate,
+            "pcg_iterations_per_step": float(np.mean(sw.pcg_its)) if sw.pcg_its else None,
+            "gpu_launches": int(launches),
+            "e2e": e2e,
+            "roofline": {"kernel": "k_spmv_sell (block-SELL SpMV inside PCG)", "bound": "hbm",
+                         "achieved": spmv.get("achieved_gbs"), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": spmv.get("frac_of_hbm_peak"), "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": spmv.get("algorithmic_bytes"),
+                         "avg_launch_ms": spmv.get("avg_ms")},
+            "kernels": kern,
+            "cpu_baseline": cb,
+            "clocks": clk,
+            "setup_s": {"mesh": round(t_mesh, 2)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "fcvm_comm_init": [ctxp, c_void_p, c_int, c_int],
     "fcvm_comm_allreduce_sum": [ctxp, c_void_p, c_int64],
     "fcvm_interface_sum": [ctxp, c_void_p],
+    "fcvm_host_alloc": [c_int64, POINTER(c_void_p)],
+    "fcvm_host_free": [c_void_p],
     "fcvm_host_update_stress_load": [ctxp, f64p, f64p, f64p, f64p, f64p, f64p, f64p, c_double, c_int, u8p],
     "fcvm_host_solve": [ctxp, f64p, f64p, c_double, c_int, POINTER(c_int), f64p],
     "fcvm_timer_start": [ctxp],

@@ -137,8 +137,7 @@ struct fcvm_ctx {
   double *if_buf = nullptr;     // [3*n_if_global]
 
   // host staging / device scratch of fcvm_host_*
-  double *stage = nullptr;
-  int64_t stage_n = 0;
+  double *gp_tmp = nullptr;     // [24*ne] device scratch of the Gauss-point layout conversions
   double *h_du = nullptr, *h_disp = nullptr, *h_qin = nullptr;
   double *diag9 = nullptr;      // [3][nn][3] assembled diagonal blocks, row-wise
 };

@@ -316,7 +316,7 @@ static void free_mesh(fcvm_ctx *c) {
   dfree(c->row_cols); dfree(c->cooK); dfree(c->minv);
   dfree(c->pcg_r); dfree(c->pcg_z); dfree(c->pcg_p); dfree(c->pcg_q);
   dfree(c->dof_weight); dfree(c->if_node); dfree(c->if_slot); dfree(c->if_buf);
-  dfree(c->h_du); dfree(c->h_disp); dfree(c->h_qin); dfree(c->diag9);
+  dfree(c->h_du); dfree(c->h_disp); dfree(c->h_qin); dfree(c->diag9); dfree(c->gp_tmp);
   c->assembled = false;
   c->have_bcs = false;
 }
@@ -332,7 +332,6 @@ extern "C" int fcvm_destroy(fcvm_ctx *c) {
   dfree(c->red_part); dfree(c->red_out); dfree(c->red_counter); dfree(c->d_arg); dfree(c->d_arg_part);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   if (c->h_arg) cudaFreeHost(c->h_arg);
-  if (c->stage) cudaFreeHost(c->stage);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->pev0); cudaEventDestroy(c->pev1);
   for (auto &s : c->prof_pool) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
   cudaStreamDestroy(c->own_stream);
@@ -736,41 +735,41 @@ extern "C" int fcvm_reaction(fcvm_ctx *c, const double *qin, double *out) {
 }
 
 // ---- Gauss-point arrays -------------------------------------------------------------------
-static int ensure_stage(fcvm_ctx *c, int64_t n) {
-  if (c->stage_n >= n) return FCVM_OK;
-  if (c->stage) cudaFreeHost(c->stage);
-  c->stage = nullptr;
-  c->stage_n = 0;
-  FCVM_CUDA(cudaMallocHost((void **)&c->stage, sizeof(double) * (size_t)n));
-  c->stage_n = n;
+static int ensure_gp_tmp(fcvm_ctx *c) {
+  if (c->gp_tmp) return FCVM_OK;
+  return dalloc(&c->gp_tmp, 24 * c->ne);
+}
+
+// pinned host memory for the callers of the fcvm_host_* entry points
+extern "C" int fcvm_host_alloc(int64_t bytes, void **out) {
+  FCVM_CHECK(out && bytes > 0, FCVM_E_ARG, "fcvm_host_alloc: bad argument");
+  FCVM_CUDA(cudaMallocHost(out, (size_t)bytes));
+  return FCVM_OK;
+}
+
+extern "C" int fcvm_host_free(void *p) {
+  if (p) FCVM_CUDA(cudaFreeHost(p));
   return FCVM_OK;
 }
 
 extern "C" int fcvm_gp_to_host(fcvm_ctx *c, const double *dev_soa, int ncomp, double *host_aos) {
   FCVM_CHECK(c && dev_soa && host_aos && (ncomp == 6 || ncomp == 1), FCVM_E_ARG, "fcvm_gp_to_host: bad argument");
   const int64_t n = 4 * c->ne * ncomp;
-  double *tmp;
-  FCVM_TRY(dalloc(&tmp, n));
-  k_gp_soa_to_aos<<<grid_for(n, 256), 256, 0, c->stream>>>(c->ne, ncomp, dev_soa, tmp);
+  FCVM_TRY(ensure_gp_tmp(c));
+  k_gp_soa_to_aos<<<grid_for(n, 256), 256, 0, c->stream>>>(c->ne, ncomp, dev_soa, c->gp_tmp);
   c->launches++;
-  int rc = fcvm_d2h(c, host_aos, tmp, sizeof(double) * n);
-  cudaFree(tmp);
-  return rc;
+  return fcvm_d2h(c, host_aos, c->gp_tmp, sizeof(double) * n);
 }
 
 extern "C" int fcvm_gp_from_host(fcvm_ctx *c, const double *host_aos, int ncomp, double *dev_soa) {
   FCVM_CHECK(c && dev_soa && host_aos && (ncomp == 6 || ncomp == 1), FCVM_E_ARG, "fcvm_gp_from_host: bad argument");
   const int64_t n = 4 * c->ne * ncomp;
-  double *tmp;
-  FCVM_TRY(dalloc(&tmp, n));
-  int rc = fcvm_h2d(c, tmp, host_aos, sizeof(double) * n);
-  if (rc == FCVM_OK) {
-    k_gp_aos_to_soa<<<grid_for(n, 256), 256, 0, c->stream>>>(c->ne, ncomp, tmp, dev_soa);
-    c->launches++;
-    cudaStreamSynchronize(c->stream);
-  }
-  cudaFree(tmp);
-  return rc;
+  FCVM_TRY(ensure_gp_tmp(c));
+  FCVM_TRY(fcvm_h2d(c, c->gp_tmp, host_aos, sizeof(double) * n));
+  k_gp_aos_to_soa<<<grid_for(n, 256), 256, 0, c->stream>>>(c->ne, ncomp, c->gp_tmp, dev_soa);
+  c->launches++;
+  FCVM_CUDA(cudaGetLastError());
+  return FCVM_OK;
 }
 
 extern "C" int fcvm_gp_fill(fcvm_ctx *c, int which, double value) {
@@ -784,14 +783,12 @@ extern "C" int fcvm_gp_fill(fcvm_ctx *c, int which, double value) {
 
 extern "C" int fcvm_pgp_to_host(fcvm_ctx *c, uint8_t *host) {
   FCVM_CHECK(c && host && c->ne > 0, FCVM_E_ARG, "fcvm_pgp_to_host: bad argument");
-  uint8_t *tmp;
-  FCVM_TRY(dalloc(&tmp, 4 * c->ne));
+  FCVM_TRY(ensure_gp_tmp(c));
+  uint8_t *tmp = (uint8_t *)c->gp_tmp;
   k_pgp_soa_to_aos<<<grid_for(4 * c->ne, 256), 256, 0, c->stream>>>(c->ne, (const uint8_t *)c->buf[FCVM_BUF_PGP],
                                                                    tmp);
   c->launches++;
-  int rc = fcvm_d2h(c, host, tmp, 4 * c->ne);
-  cudaFree(tmp);
-  return rc;
+  return fcvm_d2h(c, host, tmp, 4 * c->ne);
 }
 
 extern "C" int fcvm_pgp_count(fcvm_ctx *c, int64_t *n_plastic) {

@@ -11,15 +11,12 @@ int ensure_vec(fcvm_ctx *c, double **v, int64_t n) {
 }
 }  // namespace
 
-static double *g_unused = nullptr;
-
 // update_stress_load(gp10, elNodes, nocoord, materialbyElement, sig_yield, disp_new, du, sig,
 //                    sig_update, sig_test_global, qin, Et_E, LD, pgp)         fcVM.py:2196
 extern "C" int fcvm_host_update_stress_load(fcvm_ctx *c, const double *sig_yield, const double *disp_new,
                                             const double *du, const double *sig, double *sig_update,
                                             double *sig_test_global, double *qin, double Et_E, int LD,
                                             uint8_t *pgp) {
-  (void)g_unused;
   FCVM_CHECK(c && c->ne > 0 && sig_yield && du && sig && sig_update && sig_test_global && qin && pgp, FCVM_E_ARG,
              "fcvm_host_update_stress_load: null argument / no mesh");
   const int64_t n3 = 3 * c->nn;
@@ -30,15 +27,14 @@ extern "C" int fcvm_host_update_stress_load(fcvm_ctx *c, const double *sig_yield
   FCVM_TRY(fcvm_gp_from_host(c, sig, 6, (double *)c->buf[FCVM_BUF_SIG_OLD]));
   FCVM_TRY(fcvm_h2d(c, c->h_du, du, sizeof(double) * n3));
   if (disp_new) FCVM_TRY(fcvm_h2d(c, c->h_disp, disp_new, sizeof(double) * n3));
+  // the reference accumulates into the qin it is given (fcVM.py:2462): q = qin + assembled forces
   FCVM_TRY(fcvm_update_stress_load(c, c->h_disp, c->h_du, c->h_qin, Et_E, LD, 1.0));
+  FCVM_TRY(fcvm_h2d(c, c->h_du, qin, sizeof(double) * n3));
+  FCVM_TRY(fcvm_vec_axpby(c, n3, 1.0, c->h_du, 1.0, c->h_qin));
   FCVM_TRY(fcvm_gp_to_host(c, (const double *)c->buf[FCVM_BUF_SIG_NEW], 6, sig_update));
   FCVM_TRY(fcvm_gp_to_host(c, (const double *)c->buf[FCVM_BUF_SIG_TEST], 6, sig_test_global));
   FCVM_TRY(fcvm_pgp_to_host(c, pgp));
-  // the reference accumulates into the qin it is given (fcVM.py:2462)
-  std::vector<double> q((size_t)n3);
-  FCVM_TRY(fcvm_d2h(c, q.data(), c->h_qin, sizeof(double) * n3));
-  for (int64_t i = 0; i < n3; i++) qin[i] += q[i];
-  return FCVM_OK;
+  return fcvm_d2h(c, qin, c->h_qin, sizeof(double) * n3);
 }
 
 // x = factor(b)                                                                fcVM.py:1130, 1401

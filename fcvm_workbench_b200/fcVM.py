@@ -34,6 +34,10 @@ from .loads import surface_load_vector
 SIG_OLD, SIG_NEW, SIG_TEST, SIG_YIELD, PEEQ, CSR, TRIAX, PRESSURE, SIGMISES, ECR, PGP, MODF, GLV, FIXDOF = range(14)
 
 
+class StopAnalysis(Exception):
+    """Raised from an ``on_iteration`` hook to end the analysis early (a scripted "stop" click)."""
+
+
 def _np(a, dt):
     return np.ascontiguousarray(a, dtype=dt)
 
@@ -328,13 +332,17 @@ class Engine:
              float(Et_E), 1 if LD else 0, _ptr(pg, u8p))
         pgp[:] = pg.astype(bool)
 
-    def host_solve(self, b, rtol=1e-10, max_iter=20000):
-        x = np.empty(self.ndof)
+    def host_solve(self, b, rtol=1e-10, max_iter=20000, out=None, raise_on_noconv=True):
+        x = np.empty(self.ndof) if out is None else out
         it = ctypes.c_int()
         rr = ctypes.c_double()
-        call("fcvm_host_solve", self._ctx, _ptr(_np(b, np.float64), f64p), _ptr(x, f64p), float(rtol), int(max_iter),
-             ctypes.byref(it), ctypes.byref(rr))
+        rc = call("fcvm_host_solve", self._ctx, _ptr(_np(b, np.float64), f64p), _ptr(x, f64p), float(rtol),
+                  int(max_iter), ctypes.byref(it), ctypes.byref(rr), allow=(_lib.E_NOCONV,))
+        if rc == _lib.E_NOCONV and raise_on_noconv:
+            raise FcvmError(rc, _lib.cdll().fcvm_last_error().decode())
         self.last_solve = (it.value, rr.value)
+        self.pcg_iterations = getattr(self, "pcg_iterations", 0) + it.value
+        self.pcg_solves = getattr(self, "pcg_solves", 0) + 1
         return x
 
 
@@ -536,119 +544,125 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
     def stress_update():
         eng.update_stress_load(disp_new, du, qin, Et_E, LD)
 
-    while cnt:
-        cnt = False
-        pstep = 0
-        while pstep < nstep and not mrr:
-            step += 1
-            pstep += 1
-            restart = 0
-            say(f"Step: {step}")
-            eng.copy(du, a)                                        # a: Riks control vector
-            eng.gp_copy(SIG_NEW, SIG_OLD)
-            lbd.append(lbd[step] + dl)
-            stress_update()
-            rnorm = eng.residual(lbd[step + 1], glv, qin, r)
-            error = rnorm / qnorm
-            iterat = 0
-            say(f"Iteration: {iterat}, Error: {error:.2e}")
-            while error > error_max and not mrr:
-                iterat += 1
-                iterat_tot += 1
-                if LD and (iterat == 1 or eng.plastic_count() > 0):       # fcVM.py:1351-1396
-                    eng.put(glv, load_vector(eng.get(disp_new)))
-                    eng.assemble(glv, grav, tangent=True, disp=disp_new, Et_E=Et_E)
-                    eng.residual(1.0, glv, zero, f)
-                    eng.axpby(1.0, modf, 1.0, f)
-                    eng.solve(f, ue, rtol, max_iter)
-                    eng.copy(ue, a)
-                    eng.axpby(0.0, a, eng.norm(du) / eng.norm(a), a)      # a *= |du|/|a|
-                eng.axpby(relax, r, 0.0, f)                               # f = relax*r
-                its, _ = eng.solve(f, due, rtol, max_iter)
-                pcg_its.append(its)
-                dl = -eng.dot(a, due) / eng.dot(a, ue)                    # Riks correction, fcVM.py:1414-1417
-                lbd[step + 1] += dl
-                aa = eng.norm(a)
-                eng.axpbypcz(1.0, due, dl, ue, 1.0, du)                   # du += due + dl*ue
-                uu = eng.norm(du)
-                sf = min(aa / uu, 1.0)
-                lbd[step + 1] = lbd[step] + sf * (lbd[step + 1] - lbd[step])
-                eng.axpby(0.0, du, sf, du)                                # du *= sf
+    stopped = False
+    try:
+        while cnt:
+            cnt = False
+            pstep = 0
+            while pstep < nstep and not mrr:
+                step += 1
+                pstep += 1
+                restart = 0
+                say(f"Step: {step}")
+                eng.copy(du, a)                                        # a: Riks control vector
+                eng.gp_copy(SIG_NEW, SIG_OLD)
+                lbd.append(lbd[step] + dl)
                 stress_update()
                 rnorm = eng.residual(lbd[step + 1], glv, qin, r)
                 error = rnorm / qnorm
+                iterat = 0
                 say(f"Iteration: {iterat}, Error: {error:.2e}")
-                if on_iteration is not None:
-                    on_iteration(dict(eng=eng, step=step, iterat=iterat, iterat_tot=iterat_tot, error=error,
-                                      pcg_iterations=its, lbd=lbd))
-                if iterat > iterat_max:                                   # fcVM.py:1457-1484
-                    say(f"RESTART # {restart + 1}")
-                    if restart > 3:
-                        say("MAXIMUM RESTARTS REACHED")
-                        fail = False
-                        step -= 1
-                        lbd = lbd[:-1]
-                        mrr = True
-                    restart += 1
-                    if step > 0 and not mrr:
-                        dl = (lbd[step] - lbd[step - 1]) / scale_re / restart
-                        eng.axpbypcz(1.0 / scale_re / restart, disp_new, -1.0 / scale_re / restart, disp_old, 0.0, du)
-                    elif not mrr:
-                        dl = dl0 / scale_re / restart
-                        eng.axpby(dl / scale_re / restart, ue, 0.0, du)
-                    if not mrr:
-                        lbd[step + 1] = lbd[step] + dl
-                        stress_update()
-                        # r = fixdof*(lbd*(glv+modf) - qin): fixdof*modf is modf on free dofs
-                        eng.axpbypcz(1.0, glv, 1.0, modf, 0.0, f)
-                        rnorm = eng.residual(lbd[step + 1], f, qin, r)
-                        error = rnorm / qnorm
-                        iterat = 0
-            if abs(target_LF - lbd[step]) < abs(lbd[step + 1] - lbd[step]):           # fcVM.py:1486-1510
-                say("REACHED TARGET LOAD")
-                fac = (target_LF - lbd[step]) / (lbd[step + 1] - lbd[step])
-                eng.axpby(0.0, du, fac, du)
-                eng.scale_step_stress(fac)
-                lbd[step + 1] = target_LF
-                eng.axpby(1.0, du, 1.0, disp_new)
-                un.append(eng.max_node_disp(disp_new))
-                record()
-                iters.append(iterat)
-                nplastic.append(eng.plastic_count())
-                break
-            elif not mrr:                                                                 # fcVM.py:1515-1559
-                eng.copy(disp_new, disp_old)
-                eng.axpby(1.0, du, 1.0, disp_new)
-                dl = lbd[step + 1] - lbd[step]
-                if movdof_any:
-                    rfl.append(eng.reaction(qin))
-                if iterat > 10:
-                    dl /= scale_dn
-                    eng.axpby(0.0, du, 1.0 / scale_dn, du)
-                if iterat < 5:
-                    dl *= scale_up
-                    eng.axpby(0.0, du, scale_up, du)
-                un.append(eng.max_node_disp(disp_new))
-                record()
-                iters.append(iterat)
-                nplastic.append(eng.plastic_count())
+                while error > error_max and not mrr:
+                    iterat += 1
+                    iterat_tot += 1
+                    if LD and (iterat == 1 or eng.plastic_count() > 0):       # fcVM.py:1351-1396
+                        eng.put(glv, load_vector(eng.get(disp_new)))
+                        eng.assemble(glv, grav, tangent=True, disp=disp_new, Et_E=Et_E)
+                        eng.residual(1.0, glv, zero, f)
+                        eng.axpby(1.0, modf, 1.0, f)
+                        eng.solve(f, ue, rtol, max_iter)
+                        eng.copy(ue, a)
+                        eng.axpby(0.0, a, eng.norm(du) / eng.norm(a), a)      # a *= |du|/|a|
+                    eng.axpby(relax, r, 0.0, f)                               # f = relax*r
+                    its, _ = eng.solve(f, due, rtol, max_iter)
+                    pcg_its.append(its)
+                    dl = -eng.dot(a, due) / eng.dot(a, ue)                    # Riks correction, fcVM.py:1414-1417
+                    lbd[step + 1] += dl
+                    aa = eng.norm(a)
+                    eng.axpbypcz(1.0, due, dl, ue, 1.0, du)                   # du += due + dl*ue
+                    uu = eng.norm(du)
+                    sf = min(aa / uu, 1.0)
+                    lbd[step + 1] = lbd[step] + sf * (lbd[step + 1] - lbd[step])
+                    eng.axpby(0.0, du, sf, du)                                # du *= sf
+                    stress_update()
+                    rnorm = eng.residual(lbd[step + 1], glv, qin, r)
+                    error = rnorm / qnorm
+                    say(f"Iteration: {iterat}, Error: {error:.2e}")
+                    if on_iteration is not None:
+                        on_iteration(dict(eng=eng, step=step, iterat=iterat, iterat_tot=iterat_tot, error=error,
+                                          pcg_iterations=its, lbd=lbd))
+                    if iterat > iterat_max:                                   # fcVM.py:1457-1484
+                        say(f"RESTART # {restart + 1}")
+                        if restart > 3:
+                            say("MAXIMUM RESTARTS REACHED")
+                            fail = False
+                            step -= 1
+                            lbd = lbd[:-1]
+                            mrr = True
+                        restart += 1
+                        if step > 0 and not mrr:
+                            dl = (lbd[step] - lbd[step - 1]) / scale_re / restart
+                            eng.axpbypcz(1.0 / scale_re / restart, disp_new, -1.0 / scale_re / restart, disp_old, 0.0, du)
+                        elif not mrr:
+                            dl = dl0 / scale_re / restart
+                            eng.axpby(dl / scale_re / restart, ue, 0.0, du)
+                        if not mrr:
+                            lbd[step + 1] = lbd[step] + dl
+                            stress_update()
+                            # r = fixdof*(lbd*(glv+modf) - qin): fixdof*modf is modf on free dofs
+                            eng.axpbypcz(1.0, glv, 1.0, modf, 0.0, f)
+                            rnorm = eng.residual(lbd[step + 1], f, qin, r)
+                            error = rnorm / qnorm
+                            iterat = 0
+                if abs(target_LF - lbd[step]) < abs(lbd[step + 1] - lbd[step]):           # fcVM.py:1486-1510
+                    say("REACHED TARGET LOAD")
+                    fac = (target_LF - lbd[step]) / (lbd[step + 1] - lbd[step])
+                    eng.axpby(0.0, du, fac, du)
+                    eng.scale_step_stress(fac)
+                    lbd[step + 1] = target_LF
+                    eng.axpby(1.0, du, 1.0, disp_new)
+                    un.append(eng.max_node_disp(disp_new))
+                    record()
+                    iters.append(iterat)
+                    nplastic.append(eng.plastic_count())
+                    break
+                elif not mrr:                                                                 # fcVM.py:1515-1559
+                    eng.copy(disp_new, disp_old)
+                    eng.axpby(1.0, du, 1.0, disp_new)
+                    dl = lbd[step + 1] - lbd[step]
+                    if movdof_any:
+                        rfl.append(eng.reaction(qin))
+                    if iterat > 10:
+                        dl /= scale_dn
+                        eng.axpby(0.0, du, 1.0 / scale_dn, du)
+                    if iterat < 5:
+                        dl *= scale_up
+                        eng.axpby(0.0, du, scale_up, du)
+                    un.append(eng.max_node_disp(disp_new))
+                    record()
+                    iters.append(iterat)
+                    nplastic.append(eng.plastic_count())
+            lout = rfl if movdof_any else lbd
+            if queue and not mrr:                       # scripted stand-in for the plot window (fcVM.py:1639-2080)
+                ev = queue.pop(0)
+                tgt = target_LF
+                if isinstance(ev, tuple):
+                    ev, tgt = ev
+                if ev == "add":
+                    LF = lout[-1]
+                    if (target_LF - LF) * (tgt - LF) <= 0.0:
+                        dl = float(np.sign(tgt - LF)) * 1.0 / nstep
+                        eng.axpby(dl, ue, 0.0, du)
+                    cnt = True
+                elif ev == "rev":
+                    dl = -dl
+                    eng.axpby(0.0, du, -1.0, du)
+                    cnt = True
+                target_LF = tgt
+
+    except StopAnalysis:
+        stopped = True
         lout = rfl if movdof_any else lbd
-        if queue and not mrr:                       # scripted stand-in for the plot window (fcVM.py:1639-2080)
-            ev = queue.pop(0)
-            tgt = target_LF
-            if isinstance(ev, tuple):
-                ev, tgt = ev
-            if ev == "add":
-                LF = lout[-1]
-                if (target_LF - LF) * (tgt - LF) <= 0.0:
-                    dl = float(np.sign(tgt - LF)) * 1.0 / nstep
-                    eng.axpby(dl, ue, 0.0, du)
-                cnt = True
-            elif ev == "rev":
-                dl = -dl
-                eng.axpby(0.0, du, -1.0, du)
-                cnt = True
-            target_LF = tgt
 
     dn = eng.get(disp_new)
     dis = dn if disp_output == "total" else dn - eng.get(disp_old)
@@ -662,7 +676,7 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
                glv=eng.get(glv), modf=eng.get(modf), loadsum=tuple(loadsum), sig_yield=eng.gp_get(SIG_YIELD),
                pgp=eng.gp_get(PGP), sig_test=eng.gp_get(SIG_TEST),
                x_crip=gauss_point_coordinates(m.elNodes, m.nocoord, crip_a), ne=eng.ne, nn=eng.nn,
-               launches=eng.launch_count())
+               launches=eng.launch_count(), stopped=stopped)
     if own:
         eng.close()
     return out

@@ -167,6 +167,10 @@ int fcvm_comm_allreduce_sum(fcvm_ctx *ctx, double *dev, int64_t n);
 int fcvm_interface_sum(fcvm_ctx *ctx, double *v);
 
 /* ---- HOST-buffer drop-ins with the reference's argument lists ----------------------------- */
+/* Page-locked host memory for the arrays handed to fcvm_host_* (pageable memory works too, at
+ * roughly a third of the PCIe rate). */
+int fcvm_host_alloc(int64_t bytes, void **out);
+int fcvm_host_free(void *p);
 /* update_stress_load(gp10, elNodes, nocoord, materialbyElement, sig_yield, disp_new, du, sig,
  *                    sig_update, sig_test_global, qin, Et_E, LD, pgp)      fcVM.py:2196 */
 int fcvm_host_update_stress_load(fcvm_ctx *ctx, const double *sig_yield, const double *disp_new, const double *du,

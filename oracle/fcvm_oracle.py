@@ -226,8 +226,12 @@ def lower_csc(stm, row, col, ndof):
     return m
 
 
+class StopAnalysis(Exception):
+    """Raised from an ``on_iteration`` hook to end the run early (bench.py's bounded sample)."""
+
+
 def calcDisp(model, ctl, clicks=(), factorize: Optional[Callable] = None, log: Optional[Callable] = None,
-             gsm_out=None):
+             gsm_out=None, on_iteration: Optional[Callable] = None):
     """Load-stepping driver, restated from fcVM.py:1083-1635.
 
     ``clicks`` scripts the interactive window exactly as ``ref_harness.run_reference``.
@@ -393,6 +397,8 @@ def calcDisp(model, ctl, clicks=(), factorize: Optional[Callable] = None, log: O
                 rnorm = np.linalg.norm(r)
                 error = rnorm / qnorm
                 say(f"Iteration: {iterat}, Error: {error:.2e}")
+                if on_iteration is not None:
+                    on_iteration(dict(step=step, iterat=iterat, iterat_tot=iterat_tot, error=error))
                 if iterat > iterat_max:                                        # fcVM.py:1457-1484
                     say(f"RESTART # {restart + 1}")
                     if restart > 3:

@@ -298,3 +298,33 @@ def test_size_independent_properties_at_scale(fc):
         assert np.abs(qh.sum(axis=0)).max() < 1e-8 * np.abs(qh).sum()
         interior = np.all((m.nocoord > 1e-9) & (m.nocoord < 10.0 - 1e-9), axis=1)
         assert np.abs(qh[interior]).max() < 1e-8 * np.abs(qh).max()
+
+
+# ---- host-buffer (reference-facing) path ---------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cube2_platen", "cube2_gnly"])
+def test_host_buffer_path_matches_reference_golden(fc, name):
+    """The load-stepping driver through the HOST-buffer C ABI (what bench.py times as e2e)."""
+    from fcvm_workbench_b200.hostpath import HostEngine
+    z = load(name)
+    m, c = model_of(z), control_of(z)
+    with HostEngine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as heng:
+        o = fc.calcDisp(m, c, clicks=clicks_of(z), rtol=1e-11, engine=heng)
+        assert heng.h2d_bytes > 0 and heng.d2h_bytes > 0
+    assert list(o["iters"]) == list(z["r_iters"])
+    for k in ("lout", "un", "peeqplot", "csrplot"):
+        assert rel(o[k], z["r_" + k]) < TOL_CURVE, k
+    for k in ("displacements", "stresses", "peeq"):
+        assert rel(o[k], z["r_" + k]) < 1e-5, k
+
+
+def test_bench_workload_at_bench_tolerance_vs_oracle(fc, oracle):
+    """bench.py's workload (platen sweep) at a size the oracle handles, solved at bench.py's default PCG
+    tolerance (1e-8): same Newton iterations per step, curves within 1e-6."""
+    import bench
+    m, c = bench.workload(5)
+    ref = oracle.calcDisp(m, c)
+    o = fc.calcDisp(m, c, rtol=1e-8)
+    assert list(o["iters"]) == list(ref["iters"])
+    assert sum(o["iters"]) > 20
+    for k in ("lout", "un", "peeqplot"):
+        assert rel(o[k], ref[k]) < TOL_CURVE, k
