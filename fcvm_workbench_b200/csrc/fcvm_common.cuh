@@ -233,6 +233,82 @@ __device__ __forceinline__ void scatter_gradient(const double (&T)[3][3], double
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Run-time Gauss point: the non-zero entries of the derivative table are ten numbers that depend
+// on the point only through (xi, eta, zeta).  One code path for all four points keeps the kernel
+// small enough for the instruction cache (four compile-time copies of the stress update did not).
+// ---------------------------------------------------------------------------------------
+struct GPCoef {
+  double a4, d01, d04, d12, d16, d23, d27, x4, e4, z4;
+};
+
+__device__ __forceinline__ GPCoef gp_coef(int gp) {
+  const double xi = gp == 1 ? GP_B : GP_A, et = gp == 2 ? GP_B : GP_A, ze = gp == 3 ? GP_B : GP_A;
+  GPCoef c;
+  c.a4 = 1.0 - 4.0 * (1.0 - xi - et - ze);
+  c.d01 = 4.0 * xi - 1.0;
+  c.d04 = 4.0 * (1.0 - 2.0 * xi - et - ze);
+  c.d12 = 4.0 * et - 1.0;
+  c.d16 = 4.0 * (1.0 - xi - 2.0 * et - ze);
+  c.d23 = 4.0 * ze - 1.0;
+  c.d27 = 4.0 * (1.0 - xi - et - 2.0 * ze);
+  c.x4 = 4.0 * xi;
+  c.e4 = 4.0 * et;
+  c.z4 = 4.0 * ze;
+  return c;
+}
+
+// out[i][j] = sum_k v_k[i] * dN[j][k] with the nodal values read from a [30][stride] tile (row 3k+i)
+__device__ __forceinline__ void local_gradient_tile(const GPCoef &c, const double *tile, int stride,
+                                                    double (&out)[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double v0 = tile[(0 + i) * stride], v1 = tile[(3 + i) * stride], v2 = tile[(6 + i) * stride];
+    const double v3 = tile[(9 + i) * stride], v4 = tile[(12 + i) * stride], v5 = tile[(15 + i) * stride];
+    const double v6 = tile[(18 + i) * stride], v7 = tile[(21 + i) * stride], v8 = tile[(24 + i) * stride];
+    const double v9 = tile[(27 + i) * stride];
+    out[i][0] = c.a4 * v0 + c.d01 * v1 + c.d04 * v4 + c.e4 * (v5 - v6) + c.z4 * (v8 - v7);
+    out[i][1] = c.a4 * v0 + c.d12 * v2 + c.x4 * (v5 - v4) + c.d16 * v6 + c.z4 * (v9 - v7);
+    out[i][2] = c.a4 * v0 + c.d23 * v3 - c.x4 * v4 - c.e4 * v6 + c.d27 * v7 + c.x4 * v8 + c.e4 * v9;
+  }
+}
+
+// F[k][i] = sum_j T[i][j] * dN[j][k] stored straight to a [30][stride] tile (row 3k+i)
+__device__ __forceinline__ void store_gradient_tile(const GPCoef &c, const double (&T)[3][3], double *tile,
+                                                    int stride) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double t0 = T[i][0], t1 = T[i][1], t2 = T[i][2];
+    tile[(0 + i) * stride] = c.a4 * (t0 + t1 + t2);
+    tile[(3 + i) * stride] = c.d01 * t0;
+    tile[(6 + i) * stride] = c.d12 * t1;
+    tile[(9 + i) * stride] = c.d23 * t2;
+    tile[(12 + i) * stride] = c.d04 * t0 - c.x4 * (t1 + t2);
+    tile[(15 + i) * stride] = c.e4 * t0 + c.x4 * t1;
+    tile[(18 + i) * stride] = c.d16 * t1 - c.e4 * (t0 + t2);
+    tile[(21 + i) * stride] = c.d27 * t2 - c.z4 * (t0 + t1);
+    tile[(24 + i) * stride] = c.z4 * t0 + c.x4 * t2;
+    tile[(27 + i) * stride] = c.z4 * t1 + c.e4 * t2;
+  }
+}
+
+// determinant and inverse of the Jacobian xs[i][j] = d x_i / d xi_j   (fcVM.py:428-453)
+__device__ __forceinline__ double invert_jacobian(const double (&xs)[3][3], double (&xsi)[3][3]) {
+  double xsj = (xs[0][0] * xs[1][1] * xs[2][2] - xs[0][0] * xs[1][2] * xs[2][1] + xs[0][2] * xs[1][0] * xs[2][1] -
+                xs[0][2] * xs[1][1] * xs[2][0] + xs[0][1] * xs[1][2] * xs[2][0] - xs[0][1] * xs[1][0] * xs[2][2]);
+  double inv = 1.0 / xsj;
+  xsi[0][0] = (xs[1][1] * xs[2][2] - xs[2][1] * xs[1][2]) * inv;
+  xsi[0][1] = (xs[0][2] * xs[2][1] - xs[0][1] * xs[2][2]) * inv;
+  xsi[0][2] = (xs[0][1] * xs[1][2] - xs[0][2] * xs[1][1]) * inv;
+  xsi[1][0] = (xs[1][2] * xs[2][0] - xs[1][0] * xs[2][2]) * inv;
+  xsi[1][1] = (xs[0][0] * xs[2][2] - xs[0][2] * xs[2][0]) * inv;
+  xsi[1][2] = (xs[1][0] * xs[0][2] - xs[0][0] * xs[1][2]) * inv;
+  xsi[2][0] = (xs[1][0] * xs[2][1] - xs[2][0] * xs[1][1]) * inv;
+  xsi[2][1] = (xs[2][0] * xs[0][1] - xs[0][0] * xs[2][1]) * inv;
+  xsi[2][2] = (xs[0][0] * xs[1][1] - xs[1][0] * xs[0][1]) * inv;
+  return xsj;
+}
+
 // dN[j][k] as a compile-time constant
 template <int GP>
 __device__ __forceinline__ constexpr double dN(int j, int k) {
@@ -298,19 +374,7 @@ template <int GP>
 __device__ __forceinline__ double jacobian(const double (&X)[10][3], double (&xsi)[3][3]) {
   double xs[3][3];
   local_gradient<GP>(X, xs);
-  double xsj = (xs[0][0] * xs[1][1] * xs[2][2] - xs[0][0] * xs[1][2] * xs[2][1] + xs[0][2] * xs[1][0] * xs[2][1] -
-                xs[0][2] * xs[1][1] * xs[2][0] + xs[0][1] * xs[1][2] * xs[2][0] - xs[0][1] * xs[1][0] * xs[2][2]);
-  double inv = 1.0 / xsj;
-  xsi[0][0] = (xs[1][1] * xs[2][2] - xs[2][1] * xs[1][2]) * inv;
-  xsi[0][1] = (xs[0][2] * xs[2][1] - xs[0][1] * xs[2][2]) * inv;
-  xsi[0][2] = (xs[0][1] * xs[1][2] - xs[0][2] * xs[1][1]) * inv;
-  xsi[1][0] = (xs[1][2] * xs[2][0] - xs[1][0] * xs[2][2]) * inv;
-  xsi[1][1] = (xs[0][0] * xs[2][2] - xs[0][2] * xs[2][0]) * inv;
-  xsi[1][2] = (xs[1][0] * xs[0][2] - xs[0][0] * xs[1][2]) * inv;
-  xsi[2][0] = (xs[1][0] * xs[2][1] - xs[2][0] * xs[1][1]) * inv;
-  xsi[2][1] = (xs[2][0] * xs[0][1] - xs[0][0] * xs[2][1]) * inv;
-  xsi[2][2] = (xs[0][0] * xs[1][1] - xs[1][0] * xs[0][1]) * inv;
-  return xsj;
+  return invert_jacobian(xs, xsi);
 }
 
 // block-level deterministic sum: fixed tree over the warp, then over warps in order

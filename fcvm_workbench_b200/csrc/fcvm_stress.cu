@@ -28,29 +28,20 @@ __host__ Material make_material(double E, double nu, double Et_E) {
   return m;
 }
 
-// One Gauss point of one element: strain increment, (convected) old stress, elastic test
-// stress, radial return, contribution to the element force vector.
-template <int GP, bool LD>
-__device__ __forceinline__ void gauss_point(int64_t ne, int64_t e, const double (&X)[10][3], const double (&U)[10][3],
-                                            const Material &m, const double *__restrict__ sig_old,
-                                            const double *__restrict__ sig_yield, double yield_scale,
+constexpr int SU_E = 32;            // elements per block: one lane per element
+constexpr int SU_THREADS = 128;     // four warps: warp w integrates Gauss point w of the 32 elements
+constexpr int SU_PAD = 33;          // row stride of the force staging (conflict-free in both phases)
+
+// One Gauss point of one element (lane = element, GP = warp): (convected) old stress, elastic test
+// stress, radial return; leaves this point's share of the element force vector in shared memory.
+template <bool LD>
+__device__ __forceinline__ void gauss_point(int64_t ne, int64_t e, int GP, bool live, const GPCoef &cf,
+                                            const double (&xsi)[3][3], double xsj, const double (&g)[3][3],
+                                            double (&sc)[6], double sy, const Material &m,
                                             double *__restrict__ sig_new, double *__restrict__ sig_test,
-                                            uint8_t *__restrict__ pgp, double (&F)[10][3]) {
-  double xsi[3][3];
-  const double xsj = jacobian<GP>(X, xsi);
-  double Hl[3][3];
-  local_gradient<GP>(U, Hl);                      // Hl[i][j] = sum_k du_k[i] dN[j][k]
-  double g[3][3];                                 // g[i][mm] = d(du_i)/d x_mm
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-#pragma unroll
-    for (int mm = 0; mm < 3; mm++) g[i][mm] = Hl[i][0] * xsi[0][mm] + Hl[i][1] * xsi[1][mm] + Hl[i][2] * xsi[2][mm];
+                                            uint8_t *__restrict__ pgp, double *sF) {
   const double deps0 = g[0][0], deps1 = g[1][1], deps2 = g[2][2];
   const double deps3 = g[0][1] + g[1][0], deps4 = g[0][2] + g[2][0], deps5 = g[1][2] + g[2][1];
-
-  double sc[6];
-#pragma unroll
-  for (int c = 0; c < 6; c++) sc[c] = sig_old[((int64_t)c * 4 + GP) * ne + e];
   if (LD) {
     // convected stress sigma <- F sigma F^T / det F with F = I + grad(du)   (fcVM.py:2383-2429)
     double Fd[3][3];
@@ -78,14 +69,15 @@ __device__ __forceinline__ void gauss_point(int64_t ne, int64_t e, const double 
   double st3 = sc[3] + m.d_shear * deps3;
   double st4 = sc[4] + m.d_shear * deps4;
   double st5 = sc[5] + m.d_shear * deps5;
-  sig_test[((int64_t)0 * 4 + GP) * ne + e] = st0;
-  sig_test[((int64_t)1 * 4 + GP) * ne + e] = st1;
-  sig_test[((int64_t)2 * 4 + GP) * ne + e] = st2;
-  sig_test[((int64_t)3 * 4 + GP) * ne + e] = st3;
-  sig_test[((int64_t)4 * 4 + GP) * ne + e] = st4;
-  sig_test[((int64_t)5 * 4 + GP) * ne + e] = st5;
+  if (live) {
+    __stcs(&sig_test[((int64_t)0 * 4 + GP) * ne + e], st0);
+    __stcs(&sig_test[((int64_t)1 * 4 + GP) * ne + e], st1);
+    __stcs(&sig_test[((int64_t)2 * 4 + GP) * ne + e], st2);
+    __stcs(&sig_test[((int64_t)3 * 4 + GP) * ne + e], st3);
+    __stcs(&sig_test[((int64_t)4 * 4 + GP) * ne + e], st4);
+    __stcs(&sig_test[((int64_t)5 * 4 + GP) * ne + e], st5);
+  }
   // radial return to the von Mises surface (fcVM.py:2468-2492)
-  const double sy = yield_scale * sig_yield[(int64_t)GP * ne + e];
   const double p = (st0 + st1 + st2) / 3.0;
   st0 -= p; st1 -= p; st2 -= p;
   const double svm = sqrt(1.5 * (st0 * st0 + st1 * st1 + st2 * st2) + 3.0 * (st3 * st3 + st4 * st4 + st5 * st5));
@@ -97,14 +89,16 @@ __device__ __forceinline__ void gauss_point(int64_t ne, int64_t e, const double 
   }
   const double sxx = fac * st0 + p, syy = fac * st1 + p, szz = fac * st2 + p;
   const double sxy = fac * st3, szx = fac * st4, syz = fac * st5;
-  sig_new[((int64_t)0 * 4 + GP) * ne + e] = sxx;
-  sig_new[((int64_t)1 * 4 + GP) * ne + e] = syy;
-  sig_new[((int64_t)2 * 4 + GP) * ne + e] = szz;
-  sig_new[((int64_t)3 * 4 + GP) * ne + e] = sxy;
-  sig_new[((int64_t)4 * 4 + GP) * ne + e] = szx;
-  sig_new[((int64_t)5 * 4 + GP) * ne + e] = syz;
-  pgp[(int64_t)GP * ne + e] = pp;
-  // element force: F[k][i] += w|J| * sum_mm S[i][mm] dshpg[mm][k]   (fcVM.py:2448-2454)
+  if (live) {
+    __stcs(&sig_new[((int64_t)0 * 4 + GP) * ne + e], sxx);
+    __stcs(&sig_new[((int64_t)1 * 4 + GP) * ne + e], syy);
+    __stcs(&sig_new[((int64_t)2 * 4 + GP) * ne + e], szz);
+    __stcs(&sig_new[((int64_t)3 * 4 + GP) * ne + e], sxy);
+    __stcs(&sig_new[((int64_t)4 * 4 + GP) * ne + e], szx);
+    __stcs(&sig_new[((int64_t)5 * 4 + GP) * ne + e], syz);
+    pgp[(int64_t)GP * ne + e] = pp;
+  }
+  // element force of this Gauss point: F[k][i] = w|J| sum_mm S[i][mm] dshpg[mm][k]   (fcVM.py:2448-2454)
   const double w = GP_W * fabs(xsj);
   const double S[3][3] = {{sxx, sxy, szx}, {sxy, syy, syz}, {szx, syz, szz}};
   double T[3][3];
@@ -112,40 +106,90 @@ __device__ __forceinline__ void gauss_point(int64_t ne, int64_t e, const double 
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) T[i][j] = w * (S[i][0] * xsi[j][0] + S[i][1] * xsi[j][1] + S[i][2] * xsi[j][2]);
-  scatter_gradient<GP>(T, F);
+  store_gradient_tile(cf, T, sF, SU_PAD);
 }
 
+// Block = 32 consecutive elements x 4 Gauss points.
+//   phase 0  the 320 (element, node) pairs of the block gather coordinates and displacement
+//            increments once into shared memory ([node*3+comp][element]: conflict-free)
+//   phase 1  warp w = Gauss point w (compile-time constants per warp), lane = element: every
+//            Gauss-point array is read and written as full 256-byte lines
+//   phase 2  the 960 entries of the 32 element force vectors are summed over the Gauss points in
+//            order 0..3 (the reference's order, fcVM.py:2300) and written as one contiguous run
 template <bool LD>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SU_THREADS, LD ? 5 : 7)
 k_stress_update(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
                 const double *__restrict__ disp, const double *__restrict__ du, Material m,
                 const double *__restrict__ sig_old, const double *__restrict__ sig_yield, double yield_scale,
                 double *__restrict__ sig_new, double *__restrict__ sig_test, uint8_t *__restrict__ pgp,
                 double *__restrict__ elv) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= ne) return;
-  double X[10][3], U[10][3], F[10][3];
+  __shared__ double smem[4 * 30 * SU_PAD];        // nodal staging [2][30][32], then force staging [4][30][33]
+  double (*sX)[SU_E] = (double (*)[SU_E])smem;
+  double (*sU)[SU_E] = (double (*)[SU_E])(smem + 30 * SU_E);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t e0 = (int64_t)blockIdx.x * SU_E;
+  const bool live = e0 + lane < ne;
+  const int64_t e = min(e0 + lane, ne - 1);
+  // the Gauss-point state is requested first, so that its HBM latency overlaps the gather and the kinematics
+  double sc[6];
 #pragma unroll
-  for (int j = 0; j < 10; j++) {
-    const int64_t n3 = 3 * (int64_t)conn[(int64_t)j * ne + e];
+  for (int c = 0; c < 6; c++) sc[c] = __ldcs(&sig_old[((int64_t)c * 4 + warp) * ne + e]);
+  const double sy = yield_scale * __ldcs(&sig_yield[(int64_t)warp * ne + e]);
+  {
+    // 320 (node, element) pairs, up to three per thread; all index loads are issued before the first
+    // dependent coordinate load, all coordinate loads before the first store (two exposed latencies)
+    constexpr int NP = (10 * SU_E + SU_THREADS - 1) / SU_THREADS;
+    int64_t n3[NP];
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-      double x = xyz[n3 + i];
-      if (LD) x += disp[n3 + i];                 // updated geometry (fcVM.py:2256-2260)
-      X[j][i] = x;
-      U[j][i] = du[n3 + i];
-      F[j][i] = 0.0;
+    for (int r = 0; r < NP; r++) {
+      const int p = min(tid + r * SU_THREADS, 10 * SU_E - 1);
+      n3[r] = 3 * (int64_t)conn[(int64_t)(p >> 5) * ne + min(e0 + (p & 31), ne - 1)];
+    }
+    double xv[NP][3], uv[NP][3];
+#pragma unroll
+    for (int r = 0; r < NP; r++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        xv[r][i] = xyz[n3[r] + i];
+        if (LD) xv[r][i] += disp[n3[r] + i];     // updated geometry (fcVM.py:2256-2260)
+        uv[r][i] = du[n3[r] + i];
+      }
+#pragma unroll
+    for (int r = 0; r < NP; r++) {
+      const int p = tid + r * SU_THREADS;
+      if (p < 10 * SU_E) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          sX[3 * (p >> 5) + i][p & 31] = xv[r][i];
+          sU[3 * (p >> 5) + i][p & 31] = uv[r][i];
+        }
+      }
     }
   }
-  gauss_point<0, LD>(ne, e, X, U, m, sig_old, sig_yield, yield_scale, sig_new, sig_test, pgp, F);
-  gauss_point<1, LD>(ne, e, X, U, m, sig_old, sig_yield, yield_scale, sig_new, sig_test, pgp, F);
-  gauss_point<2, LD>(ne, e, X, U, m, sig_old, sig_yield, yield_scale, sig_new, sig_test, pgp, F);
-  gauss_point<3, LD>(ne, e, X, U, m, sig_old, sig_yield, yield_scale, sig_new, sig_test, pgp, F);
-  double *out = elv + 30 * e;
+  __syncthreads();
+  const GPCoef cf = gp_coef(warp);
+  double xsi[3][3], g[3][3], xsj;
+  {
+    double xs[3][3], Hl[3][3];
+    local_gradient_tile(cf, &sX[0][lane], SU_E, xs);
+    xsj = invert_jacobian(xs, xsi);
+    local_gradient_tile(cf, &sU[0][lane], SU_E, Hl);         // Hl[i][j] = sum_k du_k[i] dN[j][k]
 #pragma unroll
-  for (int j = 0; j < 10; j++)
+    for (int i = 0; i < 3; i++)
 #pragma unroll
-    for (int i = 0; i < 3; i++) out[3 * j + i] = F[j][i];
+      for (int mm = 0; mm < 3; mm++) g[i][mm] = Hl[i][0] * xsi[0][mm] + Hl[i][1] * xsi[1][mm] + Hl[i][2] * xsi[2][mm];
+  }
+  __syncthreads();      // every warp has consumed the staged nodal data: the force staging may overwrite it
+  gauss_point<LD>(ne, e, warp, live, cf, xsi, xsj, g, sc, sy, m, sig_new, sig_test, pgp,
+                  smem + (warp * 30) * SU_PAD + lane);
+  __syncthreads();
+  const int nlive = (int)min((int64_t)SU_E, ne - e0) * 30;
+  double *out = elv + 30 * e0;
+  for (int idx = tid; idx < nlive; idx += SU_THREADS) {
+    const int el = idx / 30, k3 = idx - 30 * el;
+    const double *f = smem + k3 * SU_PAD + el;
+    out[idx] = ((f[0] + f[30 * SU_PAD]) + f[60 * SU_PAD]) + f[90 * SU_PAD];
+  }
 }
 
 }  // namespace
@@ -186,13 +230,13 @@ extern "C" int fcvm_update_stress_load(fcvm_ctx *c, const double *disp_new, cons
   uint8_t *pg = (uint8_t *)c->buf[FCVM_BUF_PGP];
   {
     ProfScope ps(c, 1);
-    const int grid = grid_for(c->ne, 128);
+    const int grid = grid_for(c->ne, SU_E);
     if (LD)
-      k_stress_update<true><<<grid, 128, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
-                                                         yield_scale, sn, stt, pg, c->elv);
+      k_stress_update<true><<<grid, SU_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
+                                                                yield_scale, sn, stt, pg, c->elv);
     else
-      k_stress_update<false><<<grid, 128, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
-                                                          yield_scale, sn, stt, pg, c->elv);
+      k_stress_update<false><<<grid, SU_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
+                                                                 yield_scale, sn, stt, pg, c->elv);
     c->launches++;
     FCVM_CUDA(cudaGetLastError());
   }
