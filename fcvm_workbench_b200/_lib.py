@@ -67,6 +67,8 @@ _SIGNATURES = {
     "fcvm_comm_unique_id": [c_void_p],
     "fcvm_comm_init": [ctxp, c_void_p, c_int, c_int],
     "fcvm_comm_allreduce_sum": [ctxp, c_void_p, c_int64],
+    "fcvm_comm_allreduce_max": [ctxp, c_void_p, c_int64],
+    "fcvm_set_un_nodes": [ctxp, c_int64],
     "fcvm_interface_sum": [ctxp, c_void_p],
     "fcvm_host_alloc": [c_int64, POINTER(c_void_p)],
     "fcvm_host_free": [c_void_p],

@@ -108,6 +108,14 @@ int fcvm_comm_allreduce_oop(fcvm_ctx *c, const double *send, double *recv, int64
 }
 }  // namespace fcvm
 
+extern "C" int fcvm_comm_allreduce_max(fcvm_ctx *c, double *dev, int64_t n) {
+  FCVM_CHECK(c && dev && n > 0, FCVM_E_ARG, "allreduce: bad argument");
+  if (c->world <= 1) return FCVM_OK;
+  FCVM_CHECK(c->nccl_comm, FCVM_E_NCCL, "allreduce: communicator not initialised (fcvm_comm_init)");
+  FCVM_NCCL(g_nccl.AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclMax, (ncclComm_t)c->nccl_comm, c->stream));
+  return FCVM_OK;
+}
+
 extern "C" int fcvm_comm_allreduce_sum(fcvm_ctx *c, double *dev, int64_t n) {
   return fcvm::fcvm_comm_allreduce_oop(c, dev, dev, n);
 }

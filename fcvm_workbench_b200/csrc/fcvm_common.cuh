@@ -130,6 +130,7 @@ struct fcvm_ctx {
   // multi-GPU
   void *nccl_comm = nullptr;
   int rank = 0, world = 1;
+  int64_t un_nodes = -1;        // nodes entering fcvm_max_node_disp (-1: nn - 1, the reference's range)
   double *dof_weight = nullptr; // [3nn] 1/multiplicity (nullptr = 1)
   int64_t n_if_local = 0, n_if_global = 0;
   int32_t *if_node = nullptr;   // [n_if_local]

@@ -266,6 +266,7 @@ static int read_scalars(fcvm_ctx *c, int n) {
 }
 
 extern "C" int fcvm_comm_allreduce_sum(fcvm_ctx *c, double *dev, int64_t n);
+extern "C" int fcvm_comm_allreduce_max(fcvm_ctx *c, double *dev, int64_t n);
 
 static int finish_scalar(fcvm_ctx *c, int n, bool sum_over_ranks) {
   if (sum_over_ranks && c->world > 1) FCVM_TRY(fcvm_comm_allreduce_sum(c, c->red_out, n));
@@ -319,6 +320,7 @@ static void free_mesh(fcvm_ctx *c) {
   dfree(c->h_du); dfree(c->h_disp); dfree(c->h_qin); dfree(c->diag9); dfree(c->gp_tmp);
   c->assembled = false;
   c->have_bcs = false;
+  c->un_nodes = -1;
 }
 
 extern "C" int fcvm_comm_destroy_(fcvm_ctx *c);
@@ -604,6 +606,12 @@ extern "C" int fcvm_set_interface(fcvm_ctx *c, const double *dof_weight, int64_t
   return FCVM_OK;
 }
 
+extern "C" int fcvm_set_un_nodes(fcvm_ctx *c, int64_t n) {
+  FCVM_CHECK(c && c->nn > 0 && n >= 0 && n <= c->nn, FCVM_E_ARG, "fcvm_set_un_nodes: bad argument");
+  c->un_nodes = n;
+  return FCVM_OK;
+}
+
 extern "C" int fcvm_interface_sum(fcvm_ctx *c, double *v) {
   FCVM_CHECK(c && v, FCVM_E_ARG, "fcvm_interface_sum: null argument");
   if (c->world <= 1 || c->n_if_global == 0) return FCVM_OK;
@@ -713,11 +721,13 @@ extern "C" int fcvm_residual(fcvm_ctx *c, double lbd, const double *glv, const d
 
 extern "C" int fcvm_max_node_disp(fcvm_ctx *c, const double *disp, double *out) {
   FCVM_CHECK(c && disp && out, FCVM_E_ARG, "fcvm_max_node_disp: null argument");
-  // (ndof - 1) // 3 nodes, as the reference (fcVM.py:1494-1497)
-  k_max_node_disp<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>((3 * c->nn - 1) / 3, disp, c->red_part, c->red_counter,
-                                                             c->red_out);
+  // (ndof - 1) // 3 nodes, as the reference (fcVM.py:1494-1497); on a partitioned mesh the rank that
+  // holds the last global node leaves it out (fcvm_set_un_nodes) and the maximum is taken over ranks
+  const int64_t nodes = c->un_nodes >= 0 ? c->un_nodes : (3 * c->nn - 1) / 3;
+  k_max_node_disp<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(nodes, disp, c->red_part, c->red_counter, c->red_out);
   c->launches++;
   FCVM_CUDA(cudaGetLastError());
+  if (c->world > 1) FCVM_TRY(fcvm_comm_allreduce_max(c, c->red_out, 1));
   FCVM_TRY(read_scalars(c, 1));
   *out = sqrt(c->h_scalars[0]);
   return FCVM_OK;

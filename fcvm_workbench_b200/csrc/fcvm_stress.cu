@@ -30,6 +30,7 @@ __host__ Material make_material(double E, double nu, double Et_E) {
 
 constexpr int SU_E = 32;            // elements per block: one lane per element
 constexpr int SU_THREADS = 128;     // four warps: warp w integrates Gauss point w of the 32 elements
+constexpr int SU_ROW = 35;          // doubles per element of the nodal staging (30 used)
 constexpr int SU_PAD = 33;          // row stride of the force staging (conflict-free in both phases)
 
 // One Gauss point of one element (lane = element, GP = warp): (convected) old stress, elastic test
@@ -117,15 +118,14 @@ __device__ __forceinline__ void gauss_point(int64_t ne, int64_t e, int GP, bool 
 //   phase 2  the 960 entries of the 32 element force vectors are summed over the Gauss points in
 //            order 0..3 (the reference's order, fcVM.py:2300) and written as one contiguous run
 template <bool LD>
-__global__ void __launch_bounds__(SU_THREADS, LD ? 5 : 7)
+__global__ void __launch_bounds__(SU_THREADS, LD ? 5 : 6)
 k_stress_update(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
                 const double *__restrict__ disp, const double *__restrict__ du, Material m,
                 const double *__restrict__ sig_old, const double *__restrict__ sig_yield, double yield_scale,
                 double *__restrict__ sig_new, double *__restrict__ sig_test, uint8_t *__restrict__ pgp,
                 double *__restrict__ elv) {
-  __shared__ double smem[4 * 30 * SU_PAD];        // nodal staging [2][30][32], then force staging [4][30][33]
-  double (*sX)[SU_E] = (double (*)[SU_E])smem;
-  double (*sU)[SU_E] = (double (*)[SU_E])(smem + 30 * SU_E);
+  __shared__ double smem[4 * 30 * SU_PAD];        // nodal staging [2][32][35], then force staging [4][30][33]
+  double *sX = smem, *sU = smem + SU_E * SU_ROW;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t e0 = (int64_t)blockIdx.x * SU_E;
   const bool live = e0 + lane < ne;
@@ -136,33 +136,34 @@ k_stress_update(int64_t ne, const int32_t *__restrict__ conn, const double *__re
   for (int c = 0; c < 6; c++) sc[c] = __ldcs(&sig_old[((int64_t)c * 4 + warp) * ne + e]);
   const double sy = yield_scale * __ldcs(&sig_yield[(int64_t)warp * ne + e]);
   {
-    // 320 (node, element) pairs, up to three per thread; all index loads are issued before the first
-    // dependent coordinate load, all coordinate loads before the first store (two exposed latencies)
-    constexpr int NP = (10 * SU_E + SU_THREADS - 1) / SU_THREADS;
-    int64_t n3[NP];
+    // item q = 3*(32*node + element) + component, 960 per array: the three components of a node sit in
+    // adjacent lanes, so a warp-wide load touches ~11 nodal 24-byte segments instead of 32 separate
+    // ones.  All index loads are issued before the first dependent load, all loads before the first
+    // store (two exposed latencies).  Staging layout [element][SU_ROW]: conflict-free for these
+    // stores (3*el + i distinct) and for the per-element reads of phase 1 (stride 35 is odd).
+    constexpr int NQ = (30 * SU_E + SU_THREADS - 1) / SU_THREADS;
+    int64_t d[NQ];
 #pragma unroll
-    for (int r = 0; r < NP; r++) {
-      const int p = min(tid + r * SU_THREADS, 10 * SU_E - 1);
-      n3[r] = 3 * (int64_t)conn[(int64_t)(p >> 5) * ne + min(e0 + (p & 31), ne - 1)];
+    for (int r = 0; r < NQ; r++) {
+      const int q = min(tid + r * SU_THREADS, 30 * SU_E - 1);
+      const int p = q / 3;
+      d[r] = 3 * (int64_t)conn[(int64_t)(p >> 5) * ne + min(e0 + (p & 31), ne - 1)] + (q - 3 * p);
     }
-    double xv[NP][3], uv[NP][3];
+    double xv[NQ], uv[NQ];
 #pragma unroll
-    for (int r = 0; r < NP; r++)
+    for (int r = 0; r < NQ; r++) {
+      xv[r] = xyz[d[r]];
+      if (LD) xv[r] += disp[d[r]];               // updated geometry (fcVM.py:2256-2260)
+      uv[r] = du[d[r]];
+    }
 #pragma unroll
-      for (int i = 0; i < 3; i++) {
-        xv[r][i] = xyz[n3[r] + i];
-        if (LD) xv[r][i] += disp[n3[r] + i];     // updated geometry (fcVM.py:2256-2260)
-        uv[r][i] = du[n3[r] + i];
-      }
-#pragma unroll
-    for (int r = 0; r < NP; r++) {
-      const int p = tid + r * SU_THREADS;
-      if (p < 10 * SU_E) {
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          sX[3 * (p >> 5) + i][p & 31] = xv[r][i];
-          sU[3 * (p >> 5) + i][p & 31] = uv[r][i];
-        }
+    for (int r = 0; r < NQ; r++) {
+      const int q = tid + r * SU_THREADS;
+      if (q < 30 * SU_E) {
+        const int p = q / 3;
+        const int at = (p & 31) * SU_ROW + 3 * (p >> 5) + (q - 3 * p);
+        sX[at] = xv[r];
+        sU[at] = uv[r];
       }
     }
   }
@@ -171,9 +172,9 @@ k_stress_update(int64_t ne, const int32_t *__restrict__ conn, const double *__re
   double xsi[3][3], g[3][3], xsj;
   {
     double xs[3][3], Hl[3][3];
-    local_gradient_tile(cf, &sX[0][lane], SU_E, xs);
+    local_gradient_tile(cf, sX + lane * SU_ROW, 1, xs);
     xsj = invert_jacobian(xs, xsi);
-    local_gradient_tile(cf, &sU[0][lane], SU_E, Hl);         // Hl[i][j] = sum_k du_k[i] dN[j][k]
+    local_gradient_tile(cf, sU + lane * SU_ROW, 1, Hl);         // Hl[i][j] = sum_k du_k[i] dN[j][k]
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll

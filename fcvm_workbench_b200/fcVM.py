@@ -269,7 +269,14 @@ class Engine:
         arg = ctypes.c_int64()
         out = (ctypes.c_double * 7)()
         call("fcvm_update_peeq_csr", self._ctx, float(ultimate_strain), float(Et_E), ctypes.byref(arg), out)
-        return (arg.value,) + tuple(out)
+        res = (arg.value,) + tuple(out)
+        if self.comm is not None and self.comm.world > 1:
+            # global Gauss-point number = local + 4 * first element of the rank; first maximum wins (np.argmax)
+            mine = (res[0] + 4 * self.comm.elem_offset(),) + res[1:]
+            every = self.comm.allgather(mine)
+            best = max(every, key=lambda t: (t[1], -t[0]))
+            res = best[:7] + (max(t[7] for t in every),)
+        return res
 
     def scale_step_stress(self, fac):
         call("fcvm_scale_step_stress", self._ctx, float(fac))
@@ -675,7 +682,8 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
                nplastic=np.asarray(nplastic), iterat_tot=iterat_tot, pcg_iterations=np.asarray(pcg_its),
                glv=eng.get(glv), modf=eng.get(modf), loadsum=tuple(loadsum), sig_yield=eng.gp_get(SIG_YIELD),
                pgp=eng.gp_get(PGP), sig_test=eng.gp_get(SIG_TEST),
-               x_crip=gauss_point_coordinates(m.elNodes, m.nocoord, crip_a), ne=eng.ne, nn=eng.nn,
+               x_crip=(gauss_point_coordinates(m.elNodes, m.nocoord, crip_a)
+                       if getattr(eng, "comm", None) is None or eng.comm.world == 1 else None), ne=eng.ne, nn=eng.nn,
                launches=eng.launch_count(), stopped=stopped)
     if own:
         eng.close()

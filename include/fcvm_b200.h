@@ -162,6 +162,10 @@ int fcvm_map_stresses(fcvm_ctx *ctx, int averaged, double sig_yield, const int16
 int fcvm_comm_unique_id(void *id128);
 int fcvm_comm_init(fcvm_ctx *ctx, const void *id128, int rank, int world);
 int fcvm_comm_allreduce_sum(fcvm_ctx *ctx, double *dev, int64_t n);
+int fcvm_comm_allreduce_max(fcvm_ctx *ctx, double *dev, int64_t n);
+/* Number of leading local nodes that enter fcvm_max_node_disp: nn_local, minus one on the rank that
+ * holds the last global node (the reference leaves it out, fcVM.py:1494-1497). */
+int fcvm_set_un_nodes(fcvm_ctx *ctx, int64_t n);
 /* v[shared nodes] = sum over ranks (interface exchange used after SpMV and after the
  * internal-force gather). */
 int fcvm_interface_sum(fcvm_ctx *ctx, double *v);

@@ -1,0 +1,46 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/mgpu_check.py
+Every rank runs the element-partitioned load-stepping analysis; the curves must match the oracle's
+single-domain run (1e-6) with the same Newton iterations per step, shared nodes bit-identical."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from fcvm_workbench_b200 import fcVM, partition
+from fcvm_workbench_b200.control import Control
+from fcvm_workbench_b200.mesh import cube_model
+from oracle import fcvm_oracle
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for mode, kw in (("platen", dict(top_disp=0.05)), ("force", dict(top_disp=300.0))):
+    m = cube_model(4, size=8.0, mode=mode, nxyz=(4, 4, 6), **kw)
+    c = Control(sig_yield=240.0, nstep=6, error_max=1e-5, target_LF=1.5, Et_E=0.02, grav_z=-9.81 if mode == "force" else 0.0)
+    ref = fcvm_oracle.calcDisp(m, c)
+    part = partition.slab_partition(m, world)
+    lm = part.local_model(rank)
+    comm = partition.Comm(part, rank, world)
+    o = fcVM.calcDisp(lm, c, device=local, rtol=1e-11, comm=comm)
+    rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+    same_iters = list(o["iters"]) == list(ref["iters"])
+    errs = {k: rel(o[k], ref[k]) for k in ("lout", "un", "peeqplot", "csrplot")}
+    disp = part.gather_nodal(comm.allgather(o["displacements"]))
+    sig = part.gather_gauss(comm.allgather(o["stresses"]))
+    errs["displacements"] = rel(disp, ref["displacements"])
+    errs["stresses"] = rel(sig, ref["stresses"])
+    good = same_iters and all(v < 1e-6 for k, v in errs.items() if k in ("lout", "un", "peeqplot", "csrplot")) and \
+        errs["displacements"] < 1e-5 and errs["stresses"] < 1e-5
+    ok &= good
+    if rank == 0:
+        print(f"{mode}: world={world} iters {list(o['iters'])} same={same_iters} "
+              + " ".join(f"{k}={v:.1e}" for k, v in errs.items()) + (" OK" if good else " FAIL"), flush=True)
+t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if t.item() == 1.0 else 1)

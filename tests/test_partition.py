@@ -1,0 +1,134 @@
+"""Host logic of the multi-GPU path (element partition, interface maps), on the CPU.
+
+The N>1 data flow is: every rank runs the element routines on its own elements, then the shared
+nodes are completed by pack -> all-reduce -> unpack over a dense interface vector with the maps
+``Partition.interface`` hands to ``fcvm_set_interface``.  Here the element routine is the oracle and
+the all-reduce is gloo (world_size 2); the result must equal the single-domain result.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from fcvm_workbench_b200.mesh import cube_model
+from fcvm_workbench_b200.partition import slab_partition
+
+
+def _case(n=3):
+    m = cube_model(n, size=6.0, mode="platen", top_disp=0.05, nxyz=(n, n, n + 1))
+    rng = np.random.default_rng(4)
+    m.nocoord = m.nocoord + rng.uniform(-0.03, 0.03, m.nocoord.shape)
+    du = rng.normal(0, 2e-3, 3 * m.nn)
+    return m, du
+
+
+def _local_q(oracle, lm, du_local, sy=150.0):
+    ne, nn = lm.ne, lm.nn
+    out = [np.zeros(24 * ne), np.zeros(24 * ne), np.zeros(3 * nn), np.full(4 * ne, False)]
+    oracle.update_stress_load(None, lm.elNodes, lm.nocoord, lm.materialbyElement, np.full(4 * ne, sy), np.zeros(3 * nn),
+                              du_local, np.zeros(24 * ne), out[0], out[1], out[2], 0.0, False, out[3])
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_partition_covers_mesh_and_reassembles_internal_force(oracle, world):
+    m, du = _case()
+    part = slab_partition(m, world)
+    assert part.elem_start[0] == 0 and part.elem_start[-1] == m.ne
+    assert (np.diff(part.elem_start) > 0).all()
+    assert part.multiplicity.min() >= 1 and part.n_if_global > 0
+    ref = _local_q(oracle, m, du)
+    q = np.zeros((m.nn, 3))
+    wsum = np.zeros(m.nn)
+    sig, pgp = [], []
+    for r in range(world):
+        lm = part.local_model(r)
+        g = part.nodes[r]
+        assert np.array_equal(lm.nocoord, m.nocoord[g])
+        assert np.array_equal(g[lm.elNodes - 1] + 1, m.elNodes[part.elements(r)])       # same elements, same local order
+        dofs = (3 * g[:, None] + np.arange(3)).ravel()
+        assert np.array_equal(lm.fixdof, m.fixdof[dofs]) and np.array_equal(lm.movdof, m.movdof[dofs])
+        for d, v in lm.fix.items():
+            assert m.fix[int(3 * g[d // 3] + d % 3)] == v
+        assert len(lm.fix) == sum(1 for d in m.fix if (d // 3) in set(g.tolist()))
+        o = _local_q(oracle, lm, du[dofs])
+        q[g] += o[2].reshape(-1, 3)
+        w, loc, slot = part.interface(r)
+        wsum[g] += w[::3]
+        assert np.array_equal(part.if_nodes[slot], g[loc])
+        sig.append(o[0])
+        pgp.append(o[3])
+    assert np.allclose(wsum, 1.0, rtol=0, atol=1e-15)                                 # every dof counted once in dots
+    assert np.abs(q.ravel() - ref[2]).max() < 1e-12 * np.abs(ref[2]).max()
+    assert np.array_equal(part.gather_gauss(sig), ref[0]) and np.array_equal(part.gather_gauss(pgp), ref[3])
+    assert sum(part.un_nodes(r) == part.nodes[r].size - 1 for r in range(world)) == 1  # one rank drops the last node
+
+
+def test_surface_loads_go_to_the_owning_rank():
+    from fcvm_workbench_b200.loads import surface_load_vector
+    m = cube_model(3, size=6.0, mode="force", top_disp=2.5)
+    full = surface_load_vector(m.nocoord, m.loadfaces, m.pressure, m.loadvertices, m.vertexloads, m.loadedges,
+                               m.edgeloads, m.loadfaces_uni, m.faceloads)
+    part = slab_partition(m, 3)
+    acc = np.zeros((m.nn, 3))
+    nfaces = 0
+    for r in range(3):
+        lm = part.local_model(r)
+        nfaces += len(lm.loadfaces_uni) - 1
+        v = surface_load_vector(lm.nocoord, lm.loadfaces, lm.pressure, lm.loadvertices, lm.vertexloads, lm.loadedges,
+                                lm.edgeloads, lm.loadfaces_uni, lm.faceloads)
+        acc[part.nodes[r]] += v.reshape(-1, 3)
+    assert nfaces == len(m.loadfaces_uni) - 1
+    assert np.abs(acc.ravel() - full).max() < 1e-12 * np.abs(full).max()
+
+
+def _rank_main(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import fcvm_oracle as oracle
+        m, du = _case()
+        part = slab_partition(m, world)
+        lm = part.local_model(rank)
+        g = part.nodes[rank]
+        dofs = (3 * g[:, None] + np.arange(3)).ravel()
+        q = _local_q(oracle, lm, du[dofs])[2]
+        # fcvm_interface_sum on the host: pack -> all-reduce -> unpack with the maps the C library gets
+        w, loc, slot = part.interface(rank)
+        buf = torch.zeros(3 * part.n_if_global, dtype=torch.float64)
+        buf.view(-1, 3)[slot] = torch.from_numpy(q.reshape(-1, 3)[loc])
+        dist.all_reduce(buf)
+        q.reshape(-1, 3)[loc] = buf.view(-1, 3)[slot].numpy()
+        # weighted dot product, summed over ranks (fcvm_vec_dot with dof_weight)
+        d = torch.tensor([float(np.dot(w * q, q))], dtype=torch.float64)
+        dist.all_reduce(d)
+        # Newton bookkeeping that crosses ranks: first maximum in global Gauss-point numbering
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (7.5 if rank else 7.5, 4 * int(part.elem_start[rank]) + 3))
+        best = max(gathered, key=lambda t: (t[0], -t[1]))
+        np.savez(os.path.join(tmp, f"r{rank}.npz"), q=q, dot=d.numpy(), best=np.array(best))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_interface_sum_and_dots_over_gloo_world2(oracle, tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    m, du = _case()
+    ref = _local_q(oracle, m, du)[2]
+    part = slab_partition(m, world)
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        dofs = (3 * part.nodes[r][:, None] + np.arange(3)).ravel()
+        assert np.abs(z["q"] - ref[dofs]).max() < 1e-12 * np.abs(ref).max()           # shared nodes completed
+        assert abs(z["dot"][0] - np.dot(ref, ref)) < 1e-12 * np.dot(ref, ref)
+        assert z["best"][1] == 3                                                      # tie -> lowest global Gauss point
+    a, b = (np.load(tmp_path / f"r{r}.npz")["q"] for r in range(2))
+    ia = np.isin(part.nodes[0], part.if_nodes)
+    ib = np.isin(part.nodes[1], part.if_nodes)
+    assert np.array_equal(a.reshape(-1, 3)[ia], b.reshape(-1, 3)[ib])                 # bit-identical on both ranks
