@@ -236,6 +236,9 @@ def cpu_baseline(W, K, n):
 
 def main():
     a = parse()
+    if os.environ.get("FCVM_HANG_S"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["FCVM_HANG_S"]), exit=True)
     rank, world, local = dist_env()
     if a.impl == "reference":
         if rank != 0:

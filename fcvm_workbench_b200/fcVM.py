@@ -496,6 +496,10 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
     eng.assemble(glv, grav)                                        # calcGSM
     modf, fixdof = eng.buf(MODF), eng.buf(FIXDOF)
     movdof_any = bool(np.max(m.movdof) == 1)
+    cm = getattr(eng, "comm", None)
+    if cm is not None and cm.world > 1:
+        # every rank must take the same branches (they contain collectives): the flag is global
+        movdof_any = any(cm.allgather(movdof_any))
     loadsum = eng.get(glv).reshape(-1, 3).sum(axis=0)
 
     qnorm = eng.norm(glv)                                          # fcVM.py:1115-1116

@@ -6,8 +6,12 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import faulthandler
+
 import numpy as np
 import torch
+
+faulthandler.dump_traceback_later(int(os.environ.get('FCVM_HANG_S', '100')), exit=True)   # a hang prints where
 import torch.distributed as dist
 
 from fcvm_workbench_b200 import fcVM, partition
