@@ -28,6 +28,9 @@ __host__ Material make_material(double E, double nu, double Et_E) {
   return m;
 }
 
+#ifndef SU_MINBLOCKS
+#define SU_MINBLOCKS 6
+#endif
 constexpr int SU_E = 32;            // elements per block: one lane per element
 constexpr int SU_THREADS = 128;     // four warps: warp w integrates Gauss point w of the 32 elements
 constexpr int SU_ROW = 35;          // doubles per element of the nodal staging (30 used)
@@ -111,14 +114,14 @@ __device__ __forceinline__ void gauss_point(int64_t ne, int64_t e, int GP, bool 
 }
 
 // Block = 32 consecutive elements x 4 Gauss points.
-//   phase 0  the 320 (element, node) pairs of the block gather coordinates and displacement
-//            increments once into shared memory ([node*3+comp][element]: conflict-free)
-//   phase 1  warp w = Gauss point w (compile-time constants per warp), lane = element: every
-//            Gauss-point array is read and written as full 256-byte lines
+//   phase 0  coordinates and displacement increments of the 320 (element, node) pairs are gathered
+//            once into shared memory
+//   phase 1  warp w = Gauss point w (one code path, ten run-time coefficients), lane = element:
+//            every Gauss-point array is read and written as full 256-byte lines
 //   phase 2  the 960 entries of the 32 element force vectors are summed over the Gauss points in
 //            order 0..3 (the reference's order, fcVM.py:2300) and written as one contiguous run
 template <bool LD>
-__global__ void __launch_bounds__(SU_THREADS, LD ? 5 : 6)
+__global__ void __launch_bounds__(SU_THREADS, LD ? 5 : SU_MINBLOCKS)
 k_stress_update(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
                 const double *__restrict__ disp, const double *__restrict__ du, Material m,
                 const double *__restrict__ sig_old, const double *__restrict__ sig_yield, double yield_scale,
