@@ -42,7 +42,7 @@ constexpr int SELL_C = 32;           // rows per SELL slice = one warp
 constexpr int SELL_SIGMA = 4096;     // sorting window (rows)
 constexpr int RED_BLOCKS = 592;      // 4 x 148 SMs: fixed shape of every two-stage reduction
 constexpr int RED_THREADS = 256;
-constexpr int NUM_PROFILE = 5;
+constexpr int NUM_PROFILE = 7;
 
 // Gauss points of the 10-node tetrahedron (fcVM.py:589-596)
 constexpr double GP_A = 0.138196601125011;
@@ -152,11 +152,14 @@ struct ProfScope {
   fcvm_ctx *c;
   int which;
   fcvm::ProfSample *smp = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;        // synchronous mode: own pair, so scopes may nest
   ProfScope(fcvm_ctx *ctx, int w) : c(ctx), which(w) {
     if (!c->profiling) return;
     const int64_t k = c->prof.seen[which]++;
     if (c->profiling == 1) {
-      cudaEventRecord(c->pev0, c->stream);
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, c->stream);
     } else if ((k % c->prof_stride) == 0 && c->prof_used < c->prof_pool.size()) {
       smp = &c->prof_pool[c->prof_used++];
       smp->which = which;
@@ -164,13 +167,15 @@ struct ProfScope {
     }
   }
   ~ProfScope() {
-    if (c->profiling == 1) {
-      cudaEventRecord(c->pev1, c->stream);
-      cudaEventSynchronize(c->pev1);
+    if (e0) {
+      cudaEventRecord(e1, c->stream);
+      cudaEventSynchronize(e1);
       float ms = 0.f;
-      cudaEventElapsedTime(&ms, c->pev0, c->pev1);
+      cudaEventElapsedTime(&ms, e0, e1);
       c->prof.ms[which] += ms;
       c->prof.launches[which] += 1;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
     } else if (smp) {
       cudaEventRecord(smp->e1, c->stream);
     }

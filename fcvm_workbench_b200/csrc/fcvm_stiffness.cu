@@ -18,7 +18,10 @@ int launch_spmv(fcvm_ctx *c, const double *x, double *y);
 
 namespace {
 
-constexpr int KE_THREADS = 64;
+constexpr int KE_E = 32;            // elements per block: one lane per element
+constexpr int KE_THREADS = 128;     // four warps
+constexpr int KE_ROW = 35;          // doubles per element of the coordinate staging (30 used)
+constexpr int KE_PAD = 33;          // row stride of the gradient tiles
 
 struct TangentArgs {
   const double *sig_old;   // SoA
@@ -26,125 +29,151 @@ struct TangentArgs {
   double G, H;
 };
 
-template <int GP>
-__device__ __forceinline__ void store_gradients(const double (&X)[10][3], double *sm_g, double *sm_w, int tid,
-                                                double (&gam)[10]) {
-  double xsi[3][3];
-  const double xsj = jacobian<GP>(X, xsi);
-  const double w = GP_W * fabs(xsj);
-  const double sw = sqrt(w);
-  sm_w[GP * KE_THREADS + tid] = sw;
-#pragma unroll
-  for (int k = 0; k < 10; k++) {
-#pragma unroll
-    for (int mm = 0; mm < 3; mm++) {
-      double g = 0.0;
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        constexpr double zero = 0.0;
-        const double d = dN<GP>(j, k);
-        if (d != zero) g += xsi[j][mm] * d;
-      }
-      sm_g[((GP * 10 + k) * 3 + mm) * KE_THREADS + tid] = sw * g;     // sqrt(w|J|) * dN_k/dx_mm
-    }
-    gam[k] += shpN<GP>(k) * w;
-  }
-}
+// rows a of the lower block triangle handled by each warp (a+1 blocks per row): 14, 14, 14, 13 blocks
+__constant__ int c_rows[4][4] = {{9, 3, -1, -1}, {8, 4, -1, -1}, {7, 5, -1, -1}, {6, 2, 1, 0}};
 
-// One thread per element.  The scaled shape-function gradients of the four Gauss points are
-// staged in shared memory ([gp][node][dir][thread], conflict-free), then the 55 blocks
-// K_ab (a >= b) are formed as  lambda P + mu P^T + mu tr(P) I  with P = sum_gp g_a g_b^T.
+// Block = 32 consecutive elements.
+//   phase 0  nodal coordinates (+ displacements for the updated geometry) gathered once into shared memory
+//   phase A  warp w = Gauss point w, lane = element: Jacobian, then the 30 scaled shape-function
+//            gradients sqrt(w|J|) dN_k/dx_m of that point into a shared tile; weights and (tangent)
+//            the deviator / pmat factor of plastic points beside them
+//   phase B  the 55 blocks K_ab (a >= b) = lambda P + mu P^T + mu tr(P) I (- plastic correction),
+//            P = sum_gp g_a g_b^T, split over the warps by rows of equal work; each block row of 32
+//            elements x 9 entries leaves through a per-warp staging tile as one contiguous 2304-byte run
 template <bool TANGENT>
-__global__ void __launch_bounds__(KE_THREADS)
+__global__ void __launch_bounds__(KE_THREADS, 4)
 k_elem_stiffness(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
                  const double *__restrict__ disp, double lambda, double mu, TangentArgs ta, double gx, double gy,
                  double gz, double *__restrict__ cooK, double *__restrict__ elv) {
-  extern __shared__ double sm[];
-  double *sm_g = sm;                              // 120 * KE_THREADS
-  double *sm_w = sm + 120 * KE_THREADS;           // 4 * KE_THREADS
-  const int tid = threadIdx.x;
-  const int64_t e = blockIdx.x * (int64_t)KE_THREADS + tid;
-  if (e >= ne) return;
-  double gam[10];
+  __shared__ double sG[4 * 30 * KE_PAD];          // coordinate staging [32][35] first, then gradient tiles [4][30][33]
+  __shared__ double sO[4][KE_E * 9];              // per-warp output staging
+  __shared__ double sW[4][KE_E];                  // w|J| per Gauss point
+  __shared__ double sS[TANGENT ? 4 * 7 * KE_E : 1];   // [gp][6 deviator comps + factor][element]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t e0 = (int64_t)blockIdx.x * KE_E;
+  const int64_t e = min(e0 + lane, ne - 1);
   {
-    double X[10][3];
+    constexpr int NQ = (30 * KE_E + KE_THREADS - 1) / KE_THREADS;
+    int64_t d[NQ];
 #pragma unroll
-    for (int j = 0; j < 10; j++) {
-      const int64_t n3 = 3 * (int64_t)conn[(int64_t)j * ne + e];
-#pragma unroll
-      for (int i = 0; i < 3; i++) X[j][i] = xyz[n3 + i] + (disp ? disp[n3 + i] : 0.0);
-      gam[j] = 0.0;
+    for (int r = 0; r < NQ; r++) {
+      const int q = min(tid + r * KE_THREADS, 30 * KE_E - 1);
+      const int p = q / 3;
+      d[r] = 3 * (int64_t)conn[(int64_t)(p >> 5) * ne + min(e0 + (p & 31), ne - 1)] + (q - 3 * p);
     }
-    store_gradients<0>(X, sm_g, sm_w, tid, gam);
-    store_gradients<1>(X, sm_g, sm_w, tid, gam);
-    store_gradients<2>(X, sm_g, sm_w, tid, gam);
-    store_gradients<3>(X, sm_g, sm_w, tid, gam);
-  }
-  if (elv) {          // gravity: gamma[3k+i] = g_i * rho * sum_gp N_k w|J|   (fcVM.py:757-759); g pre-multiplied by rho
-    double *out = elv + 30 * e;
+    double xv[NQ];
 #pragma unroll
-    for (int k = 0; k < 10; k++) {
-      out[3 * k] = gx * gam[k];
-      out[3 * k + 1] = gy * gam[k];
-      out[3 * k + 2] = gz * gam[k];
-    }
-  }
-  // plastic Gauss points: deviator of sig_old and the factor of pmat (fcVM.py:983-997)
-  double sdev[4][6], pfac[4];
-  if (TANGENT) {
+    for (int r = 0; r < NQ; r++) xv[r] = xyz[d[r]] + (disp ? disp[d[r]] : 0.0);
 #pragma unroll
-    for (int gp = 0; gp < 4; gp++) {
-      pfac[gp] = 0.0;
-      if (ta.pgp[(int64_t)gp * ne + e]) {
-        double s[6];
-#pragma unroll
-        for (int c = 0; c < 6; c++) s[c] = ta.sig_old[((int64_t)c * 4 + gp) * ne + e];
-        const double p = (s[0] + s[1] + s[2]) / 3.0;
-        s[0] -= p; s[1] -= p; s[2] -= p;
-        double svm = sqrt(1.5 * (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) +
-                          3.0 * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5]));
-        if (svm == 0.0) svm = 1.0;
-        pfac[gp] = 3.0 * ta.G / (1.0 + ta.H / 3.0 / ta.G) / (svm * svm);
-#pragma unroll
-        for (int c = 0; c < 6; c++) sdev[gp][c] = s[c];
-      } else {
-#pragma unroll
-        for (int c = 0; c < 6; c++) sdev[gp][c] = 0.0;
+    for (int r = 0; r < NQ; r++) {
+      const int q = tid + r * KE_THREADS;
+      if (q < 30 * KE_E) {
+        const int p = q / 3;
+        sG[(p & 31) * KE_ROW + 3 * (p >> 5) + (q - 3 * p)] = xv[r];
       }
     }
   }
-  int pair = 0;
+  __syncthreads();
+  const GPCoef cf = gp_coef(warp);
+  double xsi[3][3], w;
+  {
+    double xs[3][3];
+    local_gradient_tile(cf, sG + lane * KE_ROW, 1, xs);
+    w = GP_W * fabs(invert_jacobian(xs, xsi));
+  }
+  __syncthreads();      // coordinates consumed: the gradient tiles may overwrite them
+  {
+    const double sw = sqrt(w);
+    double T[3][3];       // T[m][j] = sqrt(w|J|) * xsi[j][m]  ->  tile row 3k+m = sqrt(w|J|) dN_k/dx_m
+#pragma unroll
+    for (int mm = 0; mm < 3; mm++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) T[mm][j] = sw * xsi[j][mm];
+    store_gradient_tile(cf, T, sG + (warp * 30) * KE_PAD + lane, KE_PAD);
+    sW[warp][lane] = w;
+    if (TANGENT) {
+      // plastic Gauss points: deviator of sig_old and the factor of pmat (fcVM.py:983-997)
+      double sd[6] = {0, 0, 0, 0, 0, 0}, pf = 0.0;
+      if (ta.pgp[(int64_t)warp * ne + e]) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) sd[c] = ta.sig_old[((int64_t)c * 4 + warp) * ne + e];
+        const double p = (sd[0] + sd[1] + sd[2]) / 3.0;
+        sd[0] -= p; sd[1] -= p; sd[2] -= p;
+        double svm = sqrt(1.5 * (sd[0] * sd[0] + sd[1] * sd[1] + sd[2] * sd[2]) +
+                          3.0 * (sd[3] * sd[3] + sd[4] * sd[4] + sd[5] * sd[5]));
+        if (svm == 0.0) svm = 1.0;
+        pf = 3.0 * ta.G / (1.0 + ta.H / 3.0 / ta.G) / (svm * svm);
+      }
+#pragma unroll
+      for (int c = 0; c < 6; c++) sS[(warp * 7 + c) * KE_E + lane] = sd[c];
+      sS[(warp * 7 + 6) * KE_E + lane] = pf;
+    }
+  }
+  __syncthreads();
+  const bool live = e0 + lane < ne;
+  if (elv && warp == 3 && live) {
+    // gravity: gamma[3k+i] = g_i * rho * sum_gp N_k w|J|   (fcVM.py:757-759); g pre-multiplied by rho
+    double *out = elv + 30 * e;
+    const double w0 = sW[0][lane], w1 = sW[1][lane], w2 = sW[2][lane], w3 = sW[3][lane];
+    constexpr double A = GP_A, B = GP_B;
+    constexpr double c0 = 1.0 - 3.0 * A, c1 = 1.0 - 2.0 * A - B;     // 1 - xi - eta - zeta at point 0 / points 1..3
+    // N_k at the four points, in Gauss-point order (fcVM.py:364-380)
+    const double N[10][4] = {
+        {(2 * c0 - 1) * c0, (2 * c1 - 1) * c1, (2 * c1 - 1) * c1, (2 * c1 - 1) * c1},
+        {A * (2 * A - 1), B * (2 * B - 1), A * (2 * A - 1), A * (2 * A - 1)},
+        {A * (2 * A - 1), A * (2 * A - 1), B * (2 * B - 1), A * (2 * A - 1)},
+        {A * (2 * A - 1), A * (2 * A - 1), A * (2 * A - 1), B * (2 * B - 1)},
+        {4 * A * c0, 4 * B * c1, 4 * A * c1, 4 * A * c1},
+        {4 * A * A, 4 * B * A, 4 * A * B, 4 * A * A},
+        {4 * A * c0, 4 * A * c1, 4 * B * c1, 4 * A * c1},
+        {4 * A * c0, 4 * A * c1, 4 * A * c1, 4 * B * c1},
+        {4 * A * A, 4 * B * A, 4 * A * A, 4 * A * B},
+        {4 * A * A, 4 * A * A, 4 * B * A, 4 * A * B}};
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+      const double gam = ((N[k][0] * w0 + N[k][1] * w1) + N[k][2] * w2) + N[k][3] * w3;
+      out[3 * k] = gx * gam;
+      out[3 * k + 1] = gy * gam;
+      out[3 * k + 2] = gz * gam;
+    }
+  }
+  const int nlive9 = (int)min((int64_t)KE_E, ne - e0) * 9;
+  double *so = sO[warp];
 #pragma unroll 1
-  for (int a = 0; a < 10; a++) {
+  for (int ri = 0; ri < 4; ri++) {
+    const int a = c_rows[warp][ri];
+    if (a < 0) break;
     double ga[4][3];
 #pragma unroll
     for (int gp = 0; gp < 4; gp++)
 #pragma unroll
-      for (int mm = 0; mm < 3; mm++) ga[gp][mm] = sm_g[((gp * 10 + a) * 3 + mm) * KE_THREADS + tid];
+      for (int mm = 0; mm < 3; mm++) ga[gp][mm] = sG[(gp * 30 + 3 * a + mm) * KE_PAD + lane];
 #pragma unroll 1
-    for (int b = 0; b <= a; b++, pair++) {
+    for (int b = 0; b <= a; b++) {
       double P[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
       double Q[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
 #pragma unroll
       for (int gp = 0; gp < 4; gp++) {
         double gb[3];
 #pragma unroll
-        for (int mm = 0; mm < 3; mm++) gb[mm] = sm_g[((gp * 10 + b) * 3 + mm) * KE_THREADS + tid];
+        for (int mm = 0; mm < 3; mm++) gb[mm] = sG[(gp * 30 + 3 * b + mm) * KE_PAD + lane];
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
           for (int j = 0; j < 3; j++) P[i][j] += ga[gp][i] * gb[j];
         if (TANGENT) {
-          if (pfac[gp] != 0.0) {
+          const double f = sS[(gp * 7 + 6) * KE_E + lane];
+          if (f != 0.0) {
             // B_a^T s = S_dev g_a  (s in Voigt order xx yy zz xy zx yz)
-            const double *s = sdev[gp];
-            const double tax = s[0] * ga[gp][0] + s[3] * ga[gp][1] + s[4] * ga[gp][2];
-            const double tay = s[3] * ga[gp][0] + s[1] * ga[gp][1] + s[5] * ga[gp][2];
-            const double taz = s[4] * ga[gp][0] + s[5] * ga[gp][1] + s[2] * ga[gp][2];
-            const double tbx = s[0] * gb[0] + s[3] * gb[1] + s[4] * gb[2];
-            const double tby = s[3] * gb[0] + s[1] * gb[1] + s[5] * gb[2];
-            const double tbz = s[4] * gb[0] + s[5] * gb[1] + s[2] * gb[2];
-            const double f = pfac[gp];
+            double sd[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) sd[c] = sS[(gp * 7 + c) * KE_E + lane];
+            const double tax = sd[0] * ga[gp][0] + sd[3] * ga[gp][1] + sd[4] * ga[gp][2];
+            const double tay = sd[3] * ga[gp][0] + sd[1] * ga[gp][1] + sd[5] * ga[gp][2];
+            const double taz = sd[4] * ga[gp][0] + sd[5] * ga[gp][1] + sd[2] * ga[gp][2];
+            const double tbx = sd[0] * gb[0] + sd[3] * gb[1] + sd[4] * gb[2];
+            const double tby = sd[3] * gb[0] + sd[1] * gb[1] + sd[5] * gb[2];
+            const double tbz = sd[4] * gb[0] + sd[5] * gb[1] + sd[2] * gb[2];
             Q[0][0] += f * tax * tbx; Q[0][1] += f * tax * tby; Q[0][2] += f * tax * tbz;
             Q[1][0] += f * tay * tbx; Q[1][1] += f * tay * tby; Q[1][2] += f * tay * tbz;
             Q[2][0] += f * taz * tbx; Q[2][1] += f * taz * tby; Q[2][2] += f * taz * tbz;
@@ -152,24 +181,31 @@ k_elem_stiffness(int64_t ne, const int32_t *__restrict__ conn, const double *__r
         }
       }
       const double tr = mu * (P[0][0] + P[1][1] + P[2][2]);
-      double *out = cooK + ((int64_t)pair * ne + e) * 9;
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) {
           double v = lambda * P[i][j] + mu * P[j][i] + (i == j ? tr : 0.0);
           if (TANGENT) v -= Q[i][j];
-          out[3 * i + j] = v;
+          so[lane * 9 + 3 * i + j] = v;
         }
+      __syncwarp();
+      double *out = cooK + ((int64_t)(a * (a + 1) / 2 + b) * ne + e0) * 9;
+#pragma unroll
+      for (int m = 0; m < 9; m++) {
+        const int wd = lane + 32 * m;
+        if (wd < nlive9) __stcs(&out[wd], so[wd]);
+      }
+      __syncwarp();
     }
   }
 }
 
 // One warp per SELL slice: every stored block sums its contribution list (ascending element).
 __global__ void __launch_bounds__(SELL_C)
-k_coo_reduce(int64_t nslices, const int32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ blk_first,
-             const uint32_t *__restrict__ blk_cnt, const uint32_t *__restrict__ src,
-             const double *__restrict__ cooK, double *__restrict__ vals) {
+k_coo_reduce(int64_t nslices, const int32_t *__restrict__ slice_ptr,
+             const uint32_t *__restrict__ blk_first, const uint32_t *__restrict__ blk_cnt,
+             const uint32_t *__restrict__ src, const double *__restrict__ cooK, double *__restrict__ vals) {
   const int64_t s = blockIdx.x;
   const int lane = threadIdx.x;
   for (int32_t k = slice_ptr[s]; k < slice_ptr[s + 1]; k++) {
@@ -327,14 +363,9 @@ int run_elem_stiffness(fcvm_ctx *c, int tangent, const double *disp, double Et_E
   ta.G = E / (1.0 + nu) / 2.0;
   if (Et_E > 0.95) Et_E = 0.95;
   ta.H = (Et_E * E) / (1.0 - Et_E);
-  const size_t smem = sizeof(double) * 124 * KE_THREADS;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FCVM_CUDA(cudaFuncSetAttribute(k_elem_stiffness<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FCVM_CUDA(cudaFuncSetAttribute(k_elem_stiffness<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  const int grid = grid_for(c->ne, KE_THREADS);
+  const size_t smem = 0;
+  const int grid = grid_for(c->ne, KE_E);
+  ProfScope ps(c, 5);
   double *elv = gravity ? c->elv : nullptr;
   const double rho = c->density;
   if (tangent)
@@ -361,8 +392,11 @@ extern "C" int fcvm_assemble(fcvm_ctx *c, int tangent, const double *disp, doubl
     FCVM_TRY(launch_node_gather(c, glv, 1));       // glv += gravity  (fcVM.py:763-767)
     // shared nodes: the caller passes surface loads already summed once; gravity parts are per rank
   }
-  k_coo_reduce<<<(unsigned)c->nslices, SELL_C, 0, c->stream>>>(c->nslices, c->slice_ptr, c->blk_first, c->blk_cnt,
-                                                              c->src, c->cooK, c->vals);
+  {
+    ProfScope ps6(c, 6);
+    k_coo_reduce<<<(unsigned)c->nslices, SELL_C, 0, c->stream>>>(c->nslices, c->slice_ptr, c->blk_first, c->blk_cnt,
+                                                                c->src, c->cooK, c->vals);
+  }
   c->launches++;
   FCVM_CUDA(cudaGetLastError());
   // modf needs the unconstrained operator: K * u_fix before rows/columns are eliminated

@@ -312,7 +312,7 @@ class Engine:
 
     def profile_get(self):
         """family -> (summed ms of timed launches, timed launches, all launches)."""
-        names = ("spmv", "stress_update", "node_gather", "pcg_vector", "assembly")
+        names = ("spmv", "stress_update", "node_gather", "pcg_vector", "assembly", "elem_stiffness", "coo_reduce")
         out = {}
         for i, k in enumerate(names):
             ms = ctypes.c_double()

@@ -121,3 +121,35 @@ def top_faces(elNodes, nocoord, z, tol):
         on = np.all(np.abs(nocoord[nodes - 1, 2] - z) < tol, axis=1)
         out.append(nodes[on])
     return np.vstack(out)
+
+
+def plate_with_hole_model(nr: int = 4, nt: int = 8, nz: int = 1, L: float = 50.0, R: float = 10.0, T: float = 5.0,
+                          pull: float = 0.2, E: float = 210000.0, nu: float = 0.3, density: float = 7.85e-6,
+                          grading: float = 1.6) -> Model:
+    """Quarter of a square plate with a central circular hole, pulled in x (the analogue of the
+    reference's ``Plate_with_hole_Example``: stress concentration at the hole, mixed elastic and
+    plastic Gauss points).  The structured box mesh is mapped onto the region between the hole and
+    the outer edges; mid-side nodes follow the map, so the elements next to the hole have curved
+    edges (non-constant Jacobians).  Symmetry on x=0, y=0, z=0; ``ux = pull`` prescribed on x=L.
+    """
+    elNodes, lat = box_mesh(nr, nt, nz, 1.0, 1.0, 1.0)          # logical (s, t, zeta) in [0,1]^3
+    s = lat[:, 0] ** grading                                     # finer towards the hole
+    th = lat[:, 1] * (np.pi / 2)
+    cx, cy = np.cos(th), np.sin(th)
+    ox = np.where(th <= np.pi / 4, L, L * cx / np.maximum(cy, 1e-300))
+    oy = np.where(th <= np.pi / 4, L * cy / np.maximum(cx, 1e-300), L)
+    nocoord = np.stack([(1 - s) * R * cx + s * ox, (1 - s) * R * cy + s * oy, lat[:, 2] * T], axis=1)
+    nn = len(nocoord)
+    ids = np.arange(1, nn + 1)
+    tol = 1e-9 * L
+    x0 = ids[np.abs(nocoord[:, 0]) < tol]
+    y0 = ids[np.abs(nocoord[:, 1]) < tol]
+    z0 = ids[np.abs(nocoord[:, 2]) < tol]
+    xL = ids[np.abs(nocoord[:, 0] - L) < tol]
+    T_, F_ = True, False
+    disp = [(z0, [T_, T_, F_], [0, 0, 0]), (x0, [F_, T_, T_], [0, 0, 0]), (y0, [T_, F_, T_], [0, 0, 0]),
+            (xL, [F_, T_, T_], [pull, 0, 0])]
+    fix, fixdof, movdof = finish_bcs(nn, disp)
+    mat = np.tile(np.array([E, nu, density]), (len(elNodes), 1))
+    return Model(name=f"plate_with_hole_{nr}x{nt}x{nz}", elNodes=elNodes, nocoord=nocoord, fix=fix, fixdof=fixdof,
+                 movdof=movdof, materialbyElement=mat, noce=count_noce(elNodes, nn), **empty_loads())

@@ -188,7 +188,8 @@ int fcvm_host_solve(fcvm_ctx *ctx, const double *b, double *x, double rtol, int 
 int fcvm_timer_start(fcvm_ctx *ctx);
 int fcvm_timer_stop_ms(fcvm_ctx *ctx, float *ms);
 /* Device time per kernel family, measured with CUDA events on the launching stream;
- * which: 0 = spmv, 1 = stress update, 2 = node gather, 3 = pcg vector kernels, 4 = assembly.
+ * which: 0 = spmv, 1 = stress update, 2 = node gather, 3 = pcg vector kernels, 4 = assembly (whole call),
+ * 5 = element stiffness, 6 = COO->SELL reduction.
  * on = 0 off; 1 = every launch, synchronising after each (exact, slows the run);
  * on >= 2 = every on-th launch of a family, asynchronously (event pairs from a pool, resolved
  * when read): the timed region keeps running undisturbed.

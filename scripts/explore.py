@@ -14,6 +14,8 @@ print(f"engine setup {t2-t1:.2f}s  stats {eng.matrix_stats()}", flush=True)
 glv = eng.vec()
 eng.timer_start(); eng.assemble(glv); ms = eng.timer_stop_ms(); print(f"assemble {ms:.2f} ms")
 eng.timer_start(); eng.assemble(glv); ms = eng.timer_stop_ms(); print(f"assemble(2nd) {ms:.2f} ms")
+eng.profile(True); eng.assemble(glv); p = eng.profile_get(); eng.profile(False)
+print("assemble parts:", {k: round(v[0], 3) for k, v in p.items() if v[1]})
 x, y = eng.vec(host=np.random.default_rng(0).normal(size=eng.ndof)), eng.vec()
 for _ in range(3): eng.spmv(x, y)
 eng.timer_start()

@@ -328,3 +328,21 @@ def test_bench_workload_at_bench_tolerance_vs_oracle(fc, oracle):
     assert sum(o["iters"]) > 20
     for k in ("lout", "un", "peeqplot"):
         assert rel(o[k], ref[k]) < TOL_CURVE, k
+
+
+def test_plate_with_hole_collapse_vs_oracle(fc, oracle):
+    """BASELINE config 2 analogue: stress concentration at a hole, curved second-order elements,
+    mixed elastic/plastic Gauss points, reaction-force load-displacement curve."""
+    from fcvm_workbench_b200.control import Control
+    from fcvm_workbench_b200.mesh import plate_with_hole_model
+    m = plate_with_hole_model(5, 10, 2)
+    c = Control(sig_yield=240.0, nstep=8, error_max=1e-4, target_LF=1.0, Et_E=0.02)
+    ref = oracle.calcDisp(m, c)
+    o = fc.calcDisp(m, c, rtol=1e-11)
+    assert list(o["iters"]) == list(ref["iters"]) and sum(ref["iters"]) > 40
+    for k in ("lout", "un", "peeqplot", "csrplot", "svmplot"):
+        assert rel(o[k], ref[k]) < TOL_CURVE, k
+    assert rel(o["displacements"], ref["displacements"]) < 1e-5 and rel(o["stresses"], ref["stresses"]) < 1e-5
+    away = np.abs(svm_of(ref["sig_test"]) - ref["sig_yield"]) > BAND * ref["sig_yield"]
+    assert np.array_equal(o["pgp"][away], ref["pgp"][away])
+    assert 0.05 < o["pgp"].mean() < 0.95                                   # genuinely mixed

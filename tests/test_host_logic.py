@@ -93,3 +93,16 @@ def test_fcstd_reader_on_reference_model():
     z = load("tensile")
     assert np.array_equal(m.elNodes, z["m_elNodes"]) and np.allclose(m.nocoord, z["m_nocoord"])
     assert sorted(m.fix) == sorted(int(d) for d in z["m_fix_dof"])
+
+
+def test_plate_with_hole_mesh_is_valid_and_curved():
+    from fcvm_workbench_b200.mesh import plate_with_hole_model
+    m = plate_with_hole_model(3, 6, 1)
+    xyz = m.nocoord[m.elNodes - 1]                                          # (ne, 10, 3)
+    v = np.einsum("ei,ei->e", np.cross(xyz[:, 1] - xyz[:, 0], xyz[:, 2] - xyz[:, 0]), xyz[:, 3] - xyz[:, 0])
+    assert (v > 0).all()                                                    # positively oriented corners
+    mid01 = 0.5 * (xyz[:, 0] + xyz[:, 1])
+    assert np.abs(xyz[:, 4] - mid01).max() > 1e-3                           # mid-side nodes follow the curved map
+    r = np.hypot(m.nocoord[:, 0], m.nocoord[:, 1])
+    assert abs(r.min() - 10.0) < 1e-9 and m.nocoord[:, 0].max() == pytest.approx(50.0)
+    assert m.movdof.sum() > 0 and len(m.fix) > 0
