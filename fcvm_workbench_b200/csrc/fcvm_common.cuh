@@ -116,7 +116,8 @@ struct fcvm_ctx {
   bool assembled = false;
 
   // PCG work vectors
-  double *pcg_r = nullptr, *pcg_z = nullptr, *pcg_p = nullptr, *pcg_q = nullptr;
+  double *pcg_r = nullptr, *pcg_z = nullptr, *pcg_p = nullptr, *pcg_q = nullptr, *pcg_s = nullptr;
+  double *spmv_part = nullptr;  // block partials of the dot product fused into the SpMV
 
   // reductions
   double *red_part = nullptr;   // [8][RED_BLOCKS]

@@ -315,7 +315,7 @@ static void free_mesh(fcvm_ctx *c) {
   dfree(c->slice_ptr); dfree(c->slot_node); dfree(c->node_slot); dfree(c->colidx); dfree(c->vals);
   dfree(c->blk_first); dfree(c->blk_cnt); dfree(c->src); dfree(c->diag_pos); dfree(c->row_first);
   dfree(c->row_cols); dfree(c->cooK); dfree(c->minv);
-  dfree(c->pcg_r); dfree(c->pcg_z); dfree(c->pcg_p); dfree(c->pcg_q);
+  dfree(c->pcg_r); dfree(c->pcg_z); dfree(c->pcg_p); dfree(c->pcg_q); dfree(c->pcg_s); dfree(c->spmv_part);
   dfree(c->dof_weight); dfree(c->if_node); dfree(c->if_slot); dfree(c->if_buf);
   dfree(c->h_du); dfree(c->h_disp); dfree(c->h_qin); dfree(c->diag9); dfree(c->gp_tmp);
   c->assembled = false;
@@ -420,7 +420,7 @@ extern "C" int fcvm_set_mesh(fcvm_ctx *c, int64_t ne, int64_t nn, const int64_t 
   FCVM_CUDA(cudaMemsetAsync(c->fixval, 0, sizeof(double) * n3, st));
   FCVM_CUDA(cudaMemsetAsync(c->movmask, 0, sizeof(double) * n3, st));
   FCVM_TRY(dalloc(&c->pcg_r, n3)); FCVM_TRY(dalloc(&c->pcg_z, n3));
-  FCVM_TRY(dalloc(&c->pcg_p, n3)); FCVM_TRY(dalloc(&c->pcg_q, n3));
+  FCVM_TRY(dalloc(&c->pcg_p, n3)); FCVM_TRY(dalloc(&c->pcg_q, n3)); FCVM_TRY(dalloc(&c->pcg_s, n3));
 
   // ---- node -> (element, local node) map, ascending element within a node ---------------
   {
@@ -602,7 +602,7 @@ extern "C" int fcvm_set_interface(fcvm_ctx *c, const double *dof_weight, int64_t
     FCVM_CUDA(cudaMemcpy(c->if_node, nd.data(), sizeof(int32_t) * n_if_local, cudaMemcpyHostToDevice));
     FCVM_CUDA(cudaMemcpy(c->if_slot, sl.data(), sizeof(int32_t) * n_if_local, cudaMemcpyHostToDevice));
   }
-  if (n_if_global > 0) FCVM_TRY(dalloc(&c->if_buf, 3 * n_if_global));
+  FCVM_TRY(dalloc(&c->if_buf, 3 * n_if_global + 4));   // + tail for the PCG scalars
   return FCVM_OK;
 }
 
@@ -612,19 +612,30 @@ extern "C" int fcvm_set_un_nodes(fcvm_ctx *c, int64_t n) {
   return FCVM_OK;
 }
 
-extern "C" int fcvm_interface_sum(fcvm_ctx *c, double *v) {
+static int interface_sum_impl(fcvm_ctx *c, double *v, int tail) {
   FCVM_CHECK(c && v, FCVM_E_ARG, "fcvm_interface_sum: null argument");
-  if (c->world <= 1 || c->n_if_global == 0) return FCVM_OK;
+  if (c->world <= 1) return FCVM_OK;
+  FCVM_CHECK(c->if_buf, FCVM_E_ARG, "fcvm_interface_sum: call fcvm_set_interface first");
   cudaStream_t st = c->stream;
+  // the tail (three PCG scalars) is written by the caller before this call and must survive the clear
   FCVM_CUDA(cudaMemsetAsync(c->if_buf, 0, sizeof(double) * 3 * c->n_if_global, st));
   if (c->n_if_local > 0)
     k_if_pack<<<grid_for(3 * c->n_if_local, 256), 256, 0, st>>>(c->n_if_local, c->if_node, c->if_slot, v, c->if_buf);
-  FCVM_TRY(fcvm_comm_allreduce_sum(c, c->if_buf, 3 * c->n_if_global));
+  FCVM_TRY(fcvm_comm_allreduce_sum(c, c->if_buf, 3 * c->n_if_global + tail));
   if (c->n_if_local > 0)
     k_if_unpack<<<grid_for(3 * c->n_if_local, 256), 256, 0, st>>>(c->n_if_local, c->if_node, c->if_slot, c->if_buf,
                                                                  v);
   c->launches += 2;
   return FCVM_OK;
+}
+
+extern "C" int fcvm_interface_sum(fcvm_ctx *c, double *v) {
+  if (c && c->world > 1 && c->n_if_global == 0) return FCVM_OK;
+  return interface_sum_impl(c, v, 0);
+}
+
+namespace fcvm {
+int interface_sum_with_tail(fcvm_ctx *c, double *v) { return interface_sum_impl(c, v, 3); }
 }
 
 // ---- vectors ----------------------------------------------------------------------------
