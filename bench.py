@@ -289,7 +289,7 @@ def main():
     if rank == 0:
         clocks.start()
     eng = fcVM.Engine(model.elNodes, model.nocoord, model.materialbyElement, model.fix, device=local, comm=comm)
-    sw, out = run_sweep(model, ctl, eng, a.warmup, a.steps, a.rtol, barrier, profile_stride=32)
+    sw, out = run_sweep(model, ctl, eng, a.warmup, a.steps, a.rtol, barrier, profile_stride=31)
     ms = sw.ms
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -306,18 +306,24 @@ def main():
     eng.close()
 
     e2e = None
-    if not a.no_e2e and world == 1:
-        heng = HostEngine(model.elNodes, model.nocoord, model.materialbyElement, model.fix, device=local)
-        hs, _ = run_sweep(model, ctl, heng, a.warmup, a.steps, a.rtol)
-        e2e = {"value": 4 * ne_total * a.steps / (hs.ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int((hs.bytes1[0] - hs.bytes0[0]) / a.steps),
-               "d2h_bytes_per_step": int((hs.bytes1[1] - hs.bytes0[1]) / a.steps),
-               "ms_per_step": hs.ms / a.steps, "newton_iters_per_s": a.steps / (hs.ms * 1e-3),
-               "path": "hostpath.HostEngine: fcvm_host_solve + fcvm_host_update_stress_load on page-locked numpy arrays"}
+    if not a.no_e2e:
+        hcomm = partition.Comm(part, rank, world) if world > 1 else None
+        heng = HostEngine(model.elNodes, model.nocoord, model.materialbyElement, model.fix, device=local, comm=hcomm)
+        hs, _ = run_sweep(model, ctl, heng, a.warmup, a.steps, a.rtol, barrier)
+        hms, hb = hs.ms, [hs.bytes1[0] - hs.bytes0[0], hs.bytes1[1] - hs.bytes0[1]]
+        if world > 1:
+            t = torch.tensor([hms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            hms = float(t.item())
+            tb = torch.tensor(hb, device="cuda", dtype=torch.float64)
+            dist.all_reduce(tb)
+            hb = [float(v) for v in tb.tolist()]
+        e2e = {"value": 4 * ne_total * a.steps / (hms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(hb[0] / a.steps), "d2h_bytes_per_step": int(hb[1] / a.steps),
+               "ms_per_step": hms / a.steps, "newton_iters_per_s": a.steps / (hms * 1e-3),
+               "path": "hostpath.HostEngine: fcvm_host_solve + fcvm_host_update_stress_load on page-locked numpy arrays"
+                       + (" (per rank, bytes summed over ranks)" if world > 1 else "")}
         heng.close()
-    elif world > 1:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "host-buffer path is measured at N=1"}
 
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu:

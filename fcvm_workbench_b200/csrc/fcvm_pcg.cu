@@ -133,6 +133,7 @@ __global__ void k_pcg_scalars(double rtol, double *sc) {
   sc[S_THR] = rtol * rtol * sc[S_BB];
   sc[S_ITERS] = -1.0;
   sc[S_ALPHA] = sc[S_ALPHA + 1] = 0.0;
+  sc[S_RR + 1] = sc[S_RR];              // both parity slots start from the initial residual
 }
 
 // One iteration of the single-reduction (Chronopoulos-Gear) form of preconditioned CG, vector part:
@@ -257,8 +258,10 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
   auto spmv_dot = [&](int it_next) -> int {
     {
       ProfScope ps(c, 0);
+      // early-out test: r.r of the newest iterate whose global value is known -- the one this product
+      // belongs to on one GPU; with a communicator that sum is still in flight, so the one before
       k_spmv_sell<<<sgrid, SPMV_THREADS, 0, st>>>(c->nslices, c->slice_ptr, c->slot_node, c->colidx, c->vals, u, wv, sc,
-                                                  S_RR + (it_next & 1), c->spmv_part);
+                                                  S_RR + ((it_next + (multi ? 1 : 0)) & 1), c->spmv_part);
     }
     {
       ProfScope ps(c, 3);

@@ -31,10 +31,13 @@ _GP6 = (_fc.SIG_OLD, _fc.SIG_NEW, _fc.SIG_TEST)
 class HostEngine:
     """Same operator methods as ``fcVM.Engine``; handles are host numpy arrays."""
 
-    def __init__(self, elNodes, nocoord, materialbyElement, fix=None, device: int = 0):
-        self.dev = _fc.Engine(elNodes, nocoord, materialbyElement, fix, device=device)
+    def __init__(self, elNodes, nocoord, materialbyElement, fix=None, device: int = 0, comm=None):
+        self.dev = _fc.Engine(elNodes, nocoord, materialbyElement, fix, device=device, comm=comm)
         self.ne, self.nn, self.ndof = self.dev.ne, self.dev.nn, self.dev.ndof
-        self.comm = None
+        self.comm = comm
+        # element-partitioned run: host-side sums count shared dofs once and are completed over the ranks
+        self._w = comm.part.interface(comm.rank)[0] if comm is not None and comm.world > 1 else None
+        self._un_nodes = comm.part.un_nodes(comm.rank) if self._w is not None else None
         self._pinned = []
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -120,25 +123,33 @@ class HostEngine:
             z *= c
             z += t
 
+    def _gsum(self, v: float) -> float:
+        return float(v) if self._w is None else float(sum(self.comm.allgather(float(v))))
+
     def dot(self, x, y, n=None):
-        return float(np.dot(x, y))
+        return self._gsum(np.dot(x, y) if self._w is None else np.dot(self._w * x, y))
 
     def norm(self, x):
-        return float(np.linalg.norm(x))
+        return float(np.sqrt(self.dot(x, x)))
 
     def residual(self, lbd, glv, qin, r):
         r[:] = self._nodal[_fc.FIXDOF] * (lbd * glv - qin)
-        return float(np.linalg.norm(r))
+        return self.norm(r)
 
     def masked_norm(self, x, mask_host):
-        return float(np.linalg.norm(x * np.asarray(mask_host, dtype=np.float64)))
+        t = x * np.asarray(mask_host, dtype=np.float64)
+        return float(np.sqrt(self.dot(t, t)))
 
     def max_node_disp(self, disp):
-        d = disp[:3 * ((self.ndof - 1) // 3)].reshape(-1, 3)            # fcVM.py:1494-1497
-        return float(np.sqrt(np.max(np.sum(d * d, axis=1))))
+        nodes = (self.ndof - 1) // 3 if self._un_nodes is None else self._un_nodes      # fcVM.py:1494-1497
+        d = disp[:3 * nodes].reshape(-1, 3)
+        m = float(np.max(np.sum(d * d, axis=1))) if nodes else 0.0
+        if self._w is not None:
+            m = max(self.comm.allgather(m))
+        return float(np.sqrt(m))
 
     def reaction(self, qin):
-        return float(np.sum(self._movdof * qin))
+        return self._gsum(np.sum(self._movdof * qin) if self._w is None else np.sum(self._w * self._movdof * qin))
 
     # -- Gauss-point state on the host -------------------------------------------------------------------
     def gp_get(self, which):
@@ -156,7 +167,7 @@ class HostEngine:
         self._gp[dst][:] = self._gp[src]
 
     def plastic_count(self):
-        return int(np.count_nonzero(self._pgp))
+        return int(round(self._gsum(np.count_nonzero(self._pgp))))
 
     def scale_step_stress(self, fac):
         so = self._gp[_fc.SIG_OLD]
