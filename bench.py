@@ -236,6 +236,7 @@ def cpu_baseline(W, K, n):
 
 def main():
     a = parse()
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
     if os.environ.get("FCVM_HANG_S"):
         import faulthandler
         faulthandler.dump_traceback_later(int(os.environ["FCVM_HANG_S"]), exit=True)
