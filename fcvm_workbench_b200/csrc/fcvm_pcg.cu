@@ -18,7 +18,6 @@ int fcvm_comm_allreduce_oop(fcvm_ctx *c, const double *send, double *recv, int64
 namespace {
 
 constexpr int CHECK_EVERY = 16;
-constexpr int SPMV_THREADS = 256;
 
 // Device scalar slots in ctx->red_out.  gamma = r.u, rr = r.r and alpha live in pairs indexed by
 // the parity of the iteration; L_* are per-rank partial sums that travel with the interface
@@ -30,47 +29,65 @@ enum {
   S_DELTA = 6, S_BB = 7, S_THR = 8, S_ITERS = 9, L_RU = 10, L_RR = 11, L_WU = 12, L_BB = 13
 };
 
-// y = K x.  One thread per block row (SELL slot); a warp walks its slice column by column, so
-// the column index and each of the nine block entries are read as coalesced lines.  Matrix
-// data is streamed (evict-first) to keep x resident in L2.  With `dot_part` every warp also
-// leaves its slice's share of y.x (the w.u of the PCG iteration); k_dot_finish adds them up.
-__global__ void __launch_bounds__(SPMV_THREADS)
-k_spmv_sell(int64_t nslices, const int32_t *__restrict__ slice_ptr, const int32_t *__restrict__ slot_node,
-            const int32_t *__restrict__ colidx, const double *__restrict__ vals, const double *__restrict__ x,
-            double *__restrict__ y, const double *__restrict__ sc, int rr_slot, double *dot_part) {
-  if (sc && (sc[S_ITERS] >= 0.0 || sc[rr_slot] <= sc[S_THR])) return;   // converged: the rest of the batch is a no-op
-  const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t s = slot / SELL_C;
-  double part = 0.0;
-  if (s < nslices) {
-    const int lane = (int)(slot % SELL_C);
-    const int32_t k0 = slice_ptr[s], k1 = slice_ptr[s + 1];
-    double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-    const int32_t *ci = colidx + (int64_t)k0 * SELL_C + lane;
-    const double *v = vals + (int64_t)k0 * 9 * SELL_C + lane;
+// y = K x on the block-SELL matrix.  One block per 32-row slice, SPMV_SPLIT warps per block: warp w
+// walks columns k0+w, k0+w+SPLIT, ... of the slice, so the column index and each of the nine block
+// entries are read as coalesced 128/256-byte lines; warp 0 then adds the partial rows in warp order
+// (fixed, so bit-reproducible).  Matrix data is streamed (evict-first) to keep x resident in L2.
+// Four warps per slice keep enough loads in flight even when a rank holds only a few thousand
+// slices (one warp per slice measured 3.5 TB/s at 5k slices and 5.9 TB/s at 43k; this layout 5.2 and
+// 6.5).  With `dot_part` warp 0 also leaves the slice's share of y.x (the w.u of the PCG iteration,
+// summed by k_dot_finish).  `slices` (optional) lists the slices to process: the boundary /
+// interior split of the overlapped interface exchange.
+constexpr int SPMV_SPLIT = 4;
+__global__ void __launch_bounds__(32 * SPMV_SPLIT)
+k_spmv_sell(int64_t nlist, const int32_t *__restrict__ slices, const int32_t *__restrict__ slice_ptr,
+                  const int32_t *__restrict__ slot_node, const int32_t *__restrict__ colidx,
+                  const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+                  const double *__restrict__ sc, int rr_slot, double *dot_part) {
+  if (sc && (sc[S_ITERS] >= 0.0 || sc[rr_slot] <= sc[S_THR])) return;
+  __shared__ double part[SPMV_SPLIT - 1][3][32];
+  const int64_t s = slices ? slices[blockIdx.x] : (int64_t)blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int32_t k0 = slice_ptr[s], k1 = slice_ptr[s + 1];
+  double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+  const int32_t *ci = colidx + (int64_t)(k0 + w) * SELL_C + lane;
+  const double *v = vals + (int64_t)(k0 + w) * 9 * SELL_C + lane;
 #pragma unroll 4
-    for (int32_t k = k0; k < k1; k++, ci += SELL_C, v += 9 * SELL_C) {
-      const int64_t c3 = 3 * (int64_t)__ldcs(ci);
-      const double a0 = __ldcs(v), a1 = __ldcs(v + SELL_C), a2 = __ldcs(v + 2 * SELL_C);
-      const double a3 = __ldcs(v + 3 * SELL_C), a4 = __ldcs(v + 4 * SELL_C), a5 = __ldcs(v + 5 * SELL_C);
-      const double a6 = __ldcs(v + 6 * SELL_C), a7 = __ldcs(v + 7 * SELL_C), a8 = __ldcs(v + 8 * SELL_C);
-      const double x0 = x[c3], x1 = x[c3 + 1], x2 = x[c3 + 2];
-      y0 += a0 * x0 + a1 * x1 + a2 * x2;
-      y1 += a3 * x0 + a4 * x1 + a5 * x2;
-      y2 += a6 * x0 + a7 * x1 + a8 * x2;
-    }
-    const int32_t row = slot_node[slot];
-    if (row >= 0) {
-      const int64_t r3 = 3 * (int64_t)row;
-      y[r3] = y0;
-      y[r3 + 1] = y1;
-      y[r3 + 2] = y2;
-      if (dot_part) part = y0 * x[r3] + y1 * x[r3 + 1] + y2 * x[r3 + 2];
-    }
+  for (int32_t k = k0 + w; k < k1; k += SPMV_SPLIT, ci += SPMV_SPLIT * SELL_C, v += SPMV_SPLIT * 9 * SELL_C) {
+    const int64_t c3 = 3 * (int64_t)__ldcs(ci);
+    const double a0 = __ldcs(v), a1 = __ldcs(v + SELL_C), a2 = __ldcs(v + 2 * SELL_C);
+    const double a3 = __ldcs(v + 3 * SELL_C), a4 = __ldcs(v + 4 * SELL_C), a5 = __ldcs(v + 5 * SELL_C);
+    const double a6 = __ldcs(v + 6 * SELL_C), a7 = __ldcs(v + 7 * SELL_C), a8 = __ldcs(v + 8 * SELL_C);
+    const double x0 = x[c3], x1 = x[c3 + 1], x2 = x[c3 + 2];
+    y0 += a0 * x0 + a1 * x1 + a2 * x2;
+    y1 += a3 * x0 + a4 * x1 + a5 * x2;
+    y2 += a6 * x0 + a7 * x1 + a8 * x2;
+  }
+  if (w > 0) {
+    part[w - 1][0][lane] = y0;
+    part[w - 1][1][lane] = y1;
+    part[w - 1][2][lane] = y2;
+  }
+  __syncthreads();
+  if (w > 0) return;
+#pragma unroll
+  for (int q = 0; q < SPMV_SPLIT - 1; q++) {
+    y0 += part[q][0][lane];
+    y1 += part[q][1][lane];
+    y2 += part[q][2][lane];
+  }
+  const int32_t row = slot_node[s * SELL_C + lane];
+  double dsum = 0.0;
+  if (row >= 0) {
+    const int64_t r3 = 3 * (int64_t)row;
+    y[r3] = y0;
+    y[r3 + 1] = y1;
+    y[r3 + 2] = y2;
+    if (dot_part) dsum = y0 * x[r3] + y1 * x[r3 + 1] + y2 * x[r3 + 2];
   }
   if (dot_part) {
-    part = warp_sum(part);
-    if ((threadIdx.x & 31) == 0) dot_part[slot / SELL_C] = part;     // one partial per slice (= warp)
+    dsum = warp_sum(dsum);
+    if (lane == 0) dot_part[s] = dsum;
   }
 }
 
@@ -197,11 +214,15 @@ __global__ void k_tail_get(const double *__restrict__ tail, double *sc, int gamm
 
 }  // namespace
 
+static void spmv_launch(fcvm_ctx *c, const double *x, double *y, const double *sc, int rr_slot, double *dot_part) {
+  k_spmv_sell<<<(unsigned)c->nslices, 32 * SPMV_SPLIT, 0, c->stream>>>(
+      c->nslices, nullptr, c->slice_ptr, c->slot_node, c->colidx, c->vals, x, y, sc, rr_slot, dot_part);
+}
+
 namespace fcvm {
 int launch_spmv(fcvm_ctx *c, const double *x, double *y) {
   ProfScope ps(c, 0);
-  k_spmv_sell<<<grid_for(c->nslices * SELL_C, SPMV_THREADS), SPMV_THREADS, 0, c->stream>>>(
-      c->nslices, c->slice_ptr, c->slot_node, c->colidx, c->vals, x, y, nullptr, 0, nullptr);
+  spmv_launch(c, x, y, nullptr, 0, nullptr);
   c->launches++;
   FCVM_CUDA(cudaGetLastError());
   return FCVM_OK;
@@ -227,7 +248,6 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
   double *sc = c->red_out;
   const double *w = c->dof_weight;
   const bool multi = c->world > 1;
-  const int sgrid = grid_for(c->nslices * SELL_C, SPMV_THREADS);
   if (!c->spmv_part) {
     FCVM_CUDA(cudaMalloc((void **)&c->spmv_part, sizeof(double) * (size_t)(c->nslices + 8)));
     FCVM_CUDA(cudaMemsetAsync(c->spmv_part, 0, sizeof(double) * (size_t)(c->nslices + 8), st));
@@ -260,8 +280,7 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
       ProfScope ps(c, 0);
       // early-out test: r.r of the newest iterate whose global value is known -- the one this product
       // belongs to on one GPU; with a communicator that sum is still in flight, so the one before
-      k_spmv_sell<<<sgrid, SPMV_THREADS, 0, st>>>(c->nslices, c->slice_ptr, c->slot_node, c->colidx, c->vals, u, wv, sc,
-                                                  S_RR + ((it_next + (multi ? 1 : 0)) & 1), c->spmv_part);
+      spmv_launch(c, u, wv, sc, S_RR + ((it_next + (multi ? 1 : 0)) & 1), c->spmv_part);
     }
     {
       ProfScope ps(c, 3);
