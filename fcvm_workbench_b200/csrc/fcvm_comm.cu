@@ -83,6 +83,11 @@ extern "C" int fcvm_comm_init(fcvm_ctx *c, const void *id128, int rank, int worl
   ncclComm_t comm;
   FCVM_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
   c->nccl_comm = (void *)comm;
+  if (!c->comm_stream) {
+    FCVM_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    FCVM_CUDA(cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
+    FCVM_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+  }
   return FCVM_OK;
 }
 
@@ -95,6 +100,14 @@ extern "C" int fcvm_comm_destroy_(fcvm_ctx *c) {
 }
 
 namespace fcvm {
+int comm_allreduce_on(fcvm_ctx *c, double *dev, int64_t n, cudaStream_t st) {
+  FCVM_CHECK(c && dev && n > 0, FCVM_E_ARG, "allreduce: bad argument");
+  if (c->world <= 1) return FCVM_OK;
+  FCVM_CHECK(c->nccl_comm, FCVM_E_NCCL, "allreduce: communicator not initialised (fcvm_comm_init)");
+  FCVM_NCCL(g_nccl.AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)c->nccl_comm, st));
+  return FCVM_OK;
+}
+
 int fcvm_comm_allreduce_oop(fcvm_ctx *c, const double *send, double *recv, int64_t n) {
   FCVM_CHECK(c && send && recv && n > 0, FCVM_E_ARG, "allreduce: bad argument");
   if (c->world <= 1) {

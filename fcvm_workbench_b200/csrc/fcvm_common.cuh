@@ -137,6 +137,13 @@ struct fcvm_ctx {
   int32_t *if_node = nullptr;   // [n_if_local]
   int32_t *if_slot = nullptr;   // [n_if_local]
   double *if_buf = nullptr;     // [3*n_if_global]
+  // overlapped interface exchange of the PCG: slices holding interface rows go first, their exchange
+  // runs on comm_stream while the interior slices are multiplied
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
+  int32_t *bslices = nullptr, *islices = nullptr;
+  int64_t n_bslices = 0, n_islices = 0;
+  double *tail3 = nullptr;      // [4] per-rank PCG sums on their way through the scalar all-reduce
 
   // host staging / device scratch of fcvm_host_*
   double *gp_tmp = nullptr;     // [24*ne] device scratch of the Gauss-point layout conversions

@@ -317,6 +317,7 @@ static void free_mesh(fcvm_ctx *c) {
   dfree(c->row_cols); dfree(c->cooK); dfree(c->minv);
   dfree(c->pcg_r); dfree(c->pcg_z); dfree(c->pcg_p); dfree(c->pcg_q); dfree(c->pcg_s); dfree(c->spmv_part);
   dfree(c->dof_weight); dfree(c->if_node); dfree(c->if_slot); dfree(c->if_buf);
+  dfree(c->bslices); dfree(c->islices); dfree(c->tail3);
   dfree(c->h_du); dfree(c->h_disp); dfree(c->h_qin); dfree(c->diag9); dfree(c->gp_tmp);
   c->assembled = false;
   c->have_bcs = false;
@@ -334,6 +335,9 @@ extern "C" int fcvm_destroy(fcvm_ctx *c) {
   dfree(c->red_part); dfree(c->red_out); dfree(c->red_counter); dfree(c->d_arg); dfree(c->d_arg_part);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   if (c->h_arg) cudaFreeHost(c->h_arg);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
+  if (c->ev_halo) cudaEventDestroy(c->ev_halo);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->pev0); cudaEventDestroy(c->pev1);
   for (auto &s : c->prof_pool) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
   cudaStreamDestroy(c->own_stream);
@@ -582,6 +586,8 @@ extern "C" int fcvm_set_interface(fcvm_ctx *c, const double *dof_weight, int64_t
                                   const int64_t *if_local_node, const int64_t *if_global_slot, int64_t n_if_global) {
   FCVM_CHECK(c && c->nn > 0, FCVM_E_ARG, "fcvm_set_interface: call fcvm_set_mesh first");
   dfree(c->dof_weight); dfree(c->if_node); dfree(c->if_slot); dfree(c->if_buf);
+  dfree(c->bslices); dfree(c->islices); dfree(c->tail3);
+  c->n_bslices = c->n_islices = 0;
   const int64_t n3 = 3 * c->nn;
   if (dof_weight) {
     FCVM_TRY(dalloc(&c->dof_weight, n3));
@@ -602,7 +608,26 @@ extern "C" int fcvm_set_interface(fcvm_ctx *c, const double *dof_weight, int64_t
     FCVM_CUDA(cudaMemcpy(c->if_node, nd.data(), sizeof(int32_t) * n_if_local, cudaMemcpyHostToDevice));
     FCVM_CUDA(cudaMemcpy(c->if_slot, sl.data(), sizeof(int32_t) * n_if_local, cudaMemcpyHostToDevice));
   }
-  FCVM_TRY(dalloc(&c->if_buf, 3 * n_if_global + 4));   // + tail for the PCG scalars
+  FCVM_TRY(dalloc(&c->if_buf, 3 * n_if_global + 4));
+  FCVM_TRY(dalloc(&c->tail3, 4));
+  FCVM_CUDA(cudaMemset(c->tail3, 0, sizeof(double) * 4));
+  {
+    // slices that hold at least one interface row ("boundary") and the rest ("interior")
+    std::vector<int32_t> node_slot((size_t)c->nn);
+    FCVM_CUDA(cudaMemcpy(node_slot.data(), c->node_slot, sizeof(int32_t) * c->nn, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> isb((size_t)c->nslices, 0);
+    for (int64_t i = 0; i < n_if_local; i++) isb[(size_t)(node_slot[(size_t)if_local_node[i]] / SELL_C)] = 1;
+    std::vector<int32_t> bl, il;
+    for (int64_t s = 0; s < c->nslices; s++) (isb[(size_t)s] ? bl : il).push_back((int32_t)s);
+    c->n_bslices = (int64_t)bl.size();
+    c->n_islices = (int64_t)il.size();
+    FCVM_TRY(dalloc(&c->bslices, c->n_bslices));
+    FCVM_TRY(dalloc(&c->islices, c->n_islices));
+    if (!bl.empty())
+      FCVM_CUDA(cudaMemcpy(c->bslices, bl.data(), sizeof(int32_t) * bl.size(), cudaMemcpyHostToDevice));
+    if (!il.empty())
+      FCVM_CUDA(cudaMemcpy(c->islices, il.data(), sizeof(int32_t) * il.size(), cudaMemcpyHostToDevice));
+  }
   return FCVM_OK;
 }
 
@@ -612,16 +637,18 @@ extern "C" int fcvm_set_un_nodes(fcvm_ctx *c, int64_t n) {
   return FCVM_OK;
 }
 
-static int interface_sum_impl(fcvm_ctx *c, double *v, int tail) {
+namespace fcvm {
+int comm_allreduce_on(fcvm_ctx *c, double *dev, int64_t n, cudaStream_t st);
+}
+
+static int interface_sum_impl(fcvm_ctx *c, double *v, cudaStream_t st) {
   FCVM_CHECK(c && v, FCVM_E_ARG, "fcvm_interface_sum: null argument");
   if (c->world <= 1) return FCVM_OK;
   FCVM_CHECK(c->if_buf, FCVM_E_ARG, "fcvm_interface_sum: call fcvm_set_interface first");
-  cudaStream_t st = c->stream;
-  // the tail (three PCG scalars) is written by the caller before this call and must survive the clear
   FCVM_CUDA(cudaMemsetAsync(c->if_buf, 0, sizeof(double) * 3 * c->n_if_global, st));
   if (c->n_if_local > 0)
     k_if_pack<<<grid_for(3 * c->n_if_local, 256), 256, 0, st>>>(c->n_if_local, c->if_node, c->if_slot, v, c->if_buf);
-  FCVM_TRY(fcvm_comm_allreduce_sum(c, c->if_buf, 3 * c->n_if_global + tail));
+  FCVM_TRY(comm_allreduce_on(c, c->if_buf, 3 * c->n_if_global, st));
   if (c->n_if_local > 0)
     k_if_unpack<<<grid_for(3 * c->n_if_local, 256), 256, 0, st>>>(c->n_if_local, c->if_node, c->if_slot, c->if_buf,
                                                                  v);
@@ -631,11 +658,12 @@ static int interface_sum_impl(fcvm_ctx *c, double *v, int tail) {
 
 extern "C" int fcvm_interface_sum(fcvm_ctx *c, double *v) {
   if (c && c->world > 1 && c->n_if_global == 0) return FCVM_OK;
-  return interface_sum_impl(c, v, 0);
+  return interface_sum_impl(c, v, c->stream);
 }
 
 namespace fcvm {
-int interface_sum_with_tail(fcvm_ctx *c, double *v) { return interface_sum_impl(c, v, 3); }
+// the exchange on the communication stream (the caller orders it against the compute stream with events)
+int interface_sum_on_comm_stream(fcvm_ctx *c, double *v) { return interface_sum_impl(c, v, c->comm_stream); }
 }
 
 // ---- vectors ----------------------------------------------------------------------------

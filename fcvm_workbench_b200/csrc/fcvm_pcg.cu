@@ -47,6 +47,7 @@ k_spmv_sell(int64_t nlist, const int32_t *__restrict__ slices, const int32_t *__
   if (sc && (sc[S_ITERS] >= 0.0 || sc[rr_slot] <= sc[S_THR])) return;
   __shared__ double part[SPMV_SPLIT - 1][3][32];
   const int64_t s = slices ? slices[blockIdx.x] : (int64_t)blockIdx.x;
+  (void)nlist;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int32_t k0 = slice_ptr[s], k1 = slice_ptr[s + 1];
   double y0 = 0.0, y1 = 0.0, y2 = 0.0;
@@ -214,9 +215,12 @@ __global__ void k_tail_get(const double *__restrict__ tail, double *sc, int gamm
 
 }  // namespace
 
-static void spmv_launch(fcvm_ctx *c, const double *x, double *y, const double *sc, int rr_slot, double *dot_part) {
-  k_spmv_sell<<<(unsigned)c->nslices, 32 * SPMV_SPLIT, 0, c->stream>>>(
-      c->nslices, nullptr, c->slice_ptr, c->slot_node, c->colidx, c->vals, x, y, sc, rr_slot, dot_part);
+static void spmv_launch(fcvm_ctx *c, const double *x, double *y, const double *sc, int rr_slot, double *dot_part,
+                        const int32_t *list = nullptr, int64_t nlist = -1) {
+  const int64_t nb = list ? nlist : c->nslices;
+  if (nb <= 0) return;
+  k_spmv_sell<<<(unsigned)nb, 32 * SPMV_SPLIT, 0, c->stream>>>(nb, list, c->slice_ptr, c->slot_node, c->colidx,
+                                                              c->vals, x, y, sc, rr_slot, dot_part);
 }
 
 namespace fcvm {
@@ -236,7 +240,8 @@ extern "C" int fcvm_spmv(fcvm_ctx *c, const double *x, double *y) {
 }
 
 namespace fcvm {
-int interface_sum_with_tail(fcvm_ctx *c, double *v);
+int interface_sum_on_comm_stream(fcvm_ctx *c, double *v);
+int comm_allreduce_on(fcvm_ctx *c, double *dev, int64_t n, cudaStream_t st);
 }
 
 extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rtol, int max_iter, int use_x0,
@@ -275,24 +280,41 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
   k_pcg_scalars<<<1, 1, 0, st>>>(rtol, sc);
   c->launches++;
   // w = K u and delta = w.u; with a communicator the partial sums travel with the interface all-reduce
+  // w = K u and delta = w.u.  With a communicator the slices that hold interface rows are multiplied
+  // first; their exchange (pack, all-reduce, unpack) runs on the communication stream while the
+  // interior slices are multiplied, and only the three-scalar all-reduce stays on the critical path.
   auto spmv_dot = [&](int it_next) -> int {
-    {
+    const int flag = S_RR + ((it_next + (multi ? 1 : 0)) & 1);
+    // early-out test: r.r of the newest iterate whose global value is known -- the one this product
+    // belongs to on one GPU; with a communicator that sum is still in flight, so the one before
+    if (!multi) {
       ProfScope ps(c, 0);
-      // early-out test: r.r of the newest iterate whose global value is known -- the one this product
-      // belongs to on one GPU; with a communicator that sum is still in flight, so the one before
-      spmv_launch(c, u, wv, sc, S_RR + ((it_next + (multi ? 1 : 0)) & 1), c->spmv_part);
+      spmv_launch(c, u, wv, sc, flag, c->spmv_part);
+    } else {
+      {
+        ProfScope ps(c, 0);
+        spmv_launch(c, u, wv, sc, flag, c->spmv_part, c->bslices, c->n_bslices);
+      }
+      FCVM_CUDA(cudaEventRecord(c->ev_boundary, st));
+      FCVM_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_boundary, 0));
+      FCVM_TRY(interface_sum_on_comm_stream(c, wv));
+      FCVM_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+      {
+        ProfScope ps(c, 0);
+        spmv_launch(c, u, wv, sc, flag, c->spmv_part, c->islices, c->n_islices);
+      }
+      c->launches++;
     }
     {
       ProfScope ps(c, 3);
-      k_dot_finish<<<1, 1024, 0, st>>>(c->nslices, c->spmv_part, sc, multi ? L_WU : S_DELTA,
-                                       multi ? c->if_buf + 3 * c->n_if_global : nullptr);
+      k_dot_finish<<<1, 1024, 0, st>>>(c->nslices, c->spmv_part, sc, multi ? L_WU : S_DELTA, multi ? c->tail3 : nullptr);
     }
     c->launches += 2;
     if (multi) {
-      FCVM_TRY(interface_sum_with_tail(c, wv));
+      FCVM_TRY(comm_allreduce_on(c, c->tail3, 3, st));
+      FCVM_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
       // gamma / rr of the iterate that the next vector step will test; the first call only brings delta
-      k_tail_get<<<1, 1, 0, st>>>(c->if_buf + 3 * c->n_if_global, sc, it_next > 0 ? S_GAMMA + (it_next & 1) : -1,
-                                  S_RR + (it_next & 1));
+      k_tail_get<<<1, 1, 0, st>>>(c->tail3, sc, it_next > 0 ? S_GAMMA + (it_next & 1) : -1, S_RR + (it_next & 1));
       c->launches++;
     }
     return FCVM_OK;
