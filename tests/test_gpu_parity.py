@@ -346,3 +346,79 @@ def test_plate_with_hole_collapse_vs_oracle(fc, oracle):
     away = np.abs(svm_of(ref["sig_test"]) - ref["sig_yield"]) > BAND * ref["sig_yield"]
     assert np.array_equal(o["pgp"][away], ref["pgp"][away])
     assert 0.05 < o["pgp"].mean() < 0.95                                   # genuinely mixed
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------
+def _single_tet():
+    from fcvm_workbench_b200.mesh import box_mesh
+    el, xyz = box_mesh(1, 1, 1)
+    return el[:1].copy(), xyz
+
+
+@pytest.mark.parametrize("ne_keep", [1, 5, 33, 47])
+def test_ragged_element_counts_match_oracle(fc, oracle, ne_keep):
+    """Element counts that are not multiples of the 32-element tiles (and a single element), with the
+    unreferenced nodes that remain when elements are dropped."""
+    from fcvm_workbench_b200.mesh import cube_model
+    m = cube_model(2, size=4.0, mode="platen", top_disp=0.02)
+    rng = np.random.default_rng(ne_keep)
+    keep = np.sort(rng.choice(m.ne, size=ne_keep, replace=False))
+    el = m.elNodes[keep]
+    mat = m.materialbyElement[keep]
+    nn = m.nn
+    du = rng.normal(0, 1e-3, 3 * nn)
+    sig = rng.normal(0, 80.0, 24 * ne_keep)
+    sy = np.full(4 * ne_keep, 150.0)
+    o = [np.zeros(24 * ne_keep), np.zeros(24 * ne_keep), np.zeros(3 * nn), np.full(4 * ne_keep, False)]
+    g = [np.zeros(24 * ne_keep), np.zeros(24 * ne_keep), np.zeros(3 * nn), np.full(4 * ne_keep, False)]
+    oracle.update_stress_load(None, el, m.nocoord, mat, sy, np.zeros(3 * nn), du, sig, o[0], o[1], o[2], 0.0, False, o[3])
+    fc.update_stress_load(None, el, m.nocoord, mat, sy, np.zeros(3 * nn), du, sig, g[0], g[1], g[2], 0.0, False, g[3])
+    for a, b in zip(g[:3], o[:3]):
+        assert rel(a, b) < TOL_KERNEL
+    with fc.Engine(el, m.nocoord, mat, m.fix) as eng:
+        esm = eng.element_matrices()
+        ref = oracle.calcGSM(el, m.nocoord, mat, {}, 0, 0, 0, m.loadfaces, m.pressure, m.loadvertices, m.vertexloads,
+                             m.loadedges, m.edgeloads, m.loadfaces_uni, m.faceloads, return_esm=True)[-1]
+        assert max(rel(esm[e], ref[e]) for e in range(ne_keep)) < TOL_KERNEL
+        # nodes no kept element refers to have empty rows in the operator
+        glv = eng.vec()
+        eng.assemble(glv, (0.0, 0.0, -9.81))
+        x, y = eng.vec(host=rng.normal(size=3 * nn)), eng.vec()
+        eng.spmv(x, y)
+        used = np.zeros(nn, bool)
+        used[el.ravel() - 1] = True
+        free_unused = np.repeat(~used, 3) & (eng.fixmask == 0)
+        assert np.abs(eng.get(y)[free_unused]).max(initial=0.0) == 0.0
+
+
+def test_bad_input_is_refused_with_a_message(fc):
+    from fcvm_workbench_b200._lib import FcvmError
+    el, xyz = _single_tet()
+    bad = el.copy()
+    bad[0, 3] = len(xyz) + 5
+    with pytest.raises(FcvmError, match="outside 1"):
+        fc.Engine(bad, xyz, np.array([[210000.0, 0.3, 0.0]]), {})
+    with fc.Engine(el, xyz, np.array([[210000.0, 0.3, 0.0]]), {}) as eng:
+        x, y = eng.vec(), eng.vec()
+        with pytest.raises(FcvmError, match="assemble first"):
+            eng.spmv(x, y)
+        with pytest.raises(FcvmError, match="assemble first"):
+            eng.solve(x, y)
+
+
+def test_zero_right_hand_side_and_fully_fixed_model(fc):
+    from fcvm_workbench_b200.mesh import cube_model
+    m = cube_model(2, size=4.0, mode="platen", top_disp=0.0)
+    with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+        glv = eng.vec()
+        eng.assemble(glv)
+        b, x = eng.vec(), eng.vec(host=np.ones(eng.ndof))
+        its, rr = eng.solve(b, x)
+        assert its == 0 and rr == 0.0 and np.abs(eng.get(x)).max() == 0.0
+    fix = {d: 0.0 for d in range(3 * m.nn)}
+    with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, fix) as eng:
+        glv = eng.vec()
+        eng.assemble(glv, (0.0, 0.0, -9.81))
+        indptr, indices, data = eng.export_csc_lower()
+        assert len(indices) == 3 * m.nn and np.array_equal(indices, np.arange(3 * m.nn))     # diagonal only
+        assert np.array_equal(data, np.repeat(m.noce.astype(float), 3))                        # = elements per node
