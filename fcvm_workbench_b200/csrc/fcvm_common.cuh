@@ -145,6 +145,24 @@ struct fcvm_ctx {
   int64_t n_bslices = 0, n_islices = 0;
   double *tail3 = nullptr;      // [4] per-rank PCG sums on their way through the scalar all-reduce
 
+  // rigid-body-mode deflation of the PCG (fcvm_deflation.cu): box clusters of nodes, six modes each
+  int dn[3] = {0, 0, 0};        // clusters per direction (0 = deflation off)
+  double dlo[3] = {0, 0, 0}, dh[3] = {1, 1, 1}, dscale = 1.0;
+  int64_t ncl = 0;              // dn[0]*dn[1]*dn[2]
+  int32_t *d_cid = nullptr;     // [nn] cluster of each node
+  int32_t *cl_ptr = nullptr, *cl_nodes = nullptr;     // nodes of each cluster, ascending
+  int8_t *kz_rel = nullptr;     // [nn][8] relative position code (0..26) of the cluster a slot couples to, -1 unused
+  double *kz_val = nullptr;     // [nn][8][18] (K Z)_(i, cluster): 3 x 6
+  int32_t *ent_ptr = nullptr, *ent = nullptr;         // per target cluster: entries i*8+t, ascending
+  double *dE = nullptr, *dEinv = nullptr;             // [6 ncl][6 ncl]
+  double *d_rhs = nullptr, *d_lam = nullptr;          // [6 ncl]
+  double *spmv_part2 = nullptr; // per-slice partials of r.u
+  void *cusolver = nullptr;
+  double *cus_work = nullptr;
+  int cus_lwork = 0;
+  int *cus_info = nullptr;
+  bool defl_structure = false, defl_ready = false;
+
   // host staging / device scratch of fcvm_host_*
   double *gp_tmp = nullptr;     // [24*ne] device scratch of the Gauss-point layout conversions
   double *h_du = nullptr, *h_disp = nullptr, *h_qin = nullptr;

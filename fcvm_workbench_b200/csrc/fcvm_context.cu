@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cub/cub.cuh>
+#include <cusolverDn.h>
 #include <numeric>
 
 #include "fcvm_common.cuh"
@@ -305,7 +306,12 @@ extern "C" int fcvm_create(fcvm_ctx **out, int device) {
   return FCVM_OK;
 }
 
+namespace fcvm {
+void deflation_free(fcvm_ctx *c);
+}
+
 static void free_mesh(fcvm_ctx *c) {
+  deflation_free(c);
   dfree(c->conn); dfree(c->xyz); dfree(c->n2e_ptr); dfree(c->n2e_idx); dfree(c->elv);
   dfree(c->fixmask); dfree(c->fixval); dfree(c->movmask);
   for (int i = 0; i < FCVM_BUF_COUNT; i++) {
@@ -335,6 +341,9 @@ extern "C" int fcvm_destroy(fcvm_ctx *c) {
   dfree(c->red_part); dfree(c->red_out); dfree(c->red_counter); dfree(c->d_arg); dfree(c->d_arg_part);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   if (c->h_arg) cudaFreeHost(c->h_arg);
+  if (c->cusolver) cusolverDnDestroy((cusolverDnHandle_t)c->cusolver);
+  if (c->cus_work) cudaFree(c->cus_work);
+  if (c->cus_info) cudaFree(c->cus_info);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);

@@ -1,0 +1,412 @@
+// Rigid-body-mode deflation of the preconditioned CG solve (second level of the preconditioner).
+//
+// Block-Jacobi PCG needs O(L/h) iterations on an elasticity problem because the smooth, low-energy
+// displacement fields are only reached slowly.  Here the nodes are grouped into box clusters and
+// the six rigid-body modes of every cluster (three translations, three rotations about the box
+// centre, rows of prescribed dofs zeroed) span a coarse space Z.  With E = Z^T K Z (dense, a few
+// thousand unknowns, inverted once per assembly) the preconditioner becomes
+//     u = y + Z E^-1 (Z^T r - (K Z)^T y),   y = D^-1 r          ("A-DEF2", Tang/Nabben/Vuik/Erlangga 2009)
+// and the start vector x0 + Z E^-1 Z^T (b - K x0); the iteration count then scales with the cluster
+// size H/h instead of the domain size L/h.  Everything is deterministic: fixed lists, fixed-shape
+// reductions, no floating-point atomics.  K Z is stored sparsely per node (a node couples to at most
+// 2 x 2 x 2 clusters because a cluster is at least one element wide).
+#include <cusolverDn.h>
+
+#include <algorithm>
+
+#include "fcvm_common.cuh"
+#include "fcvm_reduce.cuh"
+
+using namespace fcvm;
+
+extern "C" int fcvm_comm_allreduce_sum(fcvm_ctx *c, double *dev, int64_t n);
+
+namespace {
+
+struct Grid {
+  int n[3];
+  double lo[3], h[3], scale;
+};
+
+// Z_j: 3 x 6 = [ I | (e_k x rel)/scale ], rows of prescribed dofs zeroed
+__device__ __forceinline__ void z_of(const Grid &g, int32_t cl, const double *__restrict__ xyz, const double *__restrict__ fixdof,
+                                     int64_t j, double (&Z)[3][6]) {
+  const int ix = cl % g.n[0], iy = (cl / g.n[0]) % g.n[1], iz = cl / (g.n[0] * g.n[1]);
+  const double rx = (xyz[3 * j] - (g.lo[0] + (ix + 0.5) * g.h[0])) / g.scale;
+  const double ry = (xyz[3 * j + 1] - (g.lo[1] + (iy + 0.5) * g.h[1])) / g.scale;
+  const double rz = (xyz[3 * j + 2] - (g.lo[2] + (iz + 0.5) * g.h[2])) / g.scale;
+  const double f0 = fixdof[3 * j], f1 = fixdof[3 * j + 1], f2 = fixdof[3 * j + 2];
+  // e_x x r = (0, -rz, ry), e_y x r = (rz, 0, -rx), e_z x r = (-ry, rx, 0)
+  Z[0][0] = f0; Z[0][1] = 0;  Z[0][2] = 0;  Z[0][3] = 0;        Z[0][4] = f0 * rz;  Z[0][5] = -f0 * ry;
+  Z[1][0] = 0;  Z[1][1] = f1; Z[1][2] = 0;  Z[1][3] = -f1 * rz; Z[1][4] = 0;        Z[1][5] = f1 * rx;
+  Z[2][0] = 0;  Z[2][1] = 0;  Z[2][2] = f2; Z[2][3] = f2 * ry;  Z[2][4] = -f2 * rx; Z[2][5] = 0;
+}
+
+__device__ __forceinline__ int rel_code(const Grid &g, int32_t from, int32_t to) {
+  const int nx = g.n[0], ny = g.n[1];
+  const int dx = to % nx - from % nx, dy = (to / nx) % ny - (from / nx) % ny, dz = to / (nx * ny) - from / (nx * ny);
+  if (dx < -1 || dx > 1 || dy < -1 || dy > 1 || dz < -1 || dz > 1) return -1;
+  return (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1);
+}
+
+__device__ __forceinline__ int32_t neighbour(const Grid &g, int32_t cl, int code) {
+  const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+  const int ix = cl % nx + code % 3 - 1, iy = (cl / nx) % ny + (code / 3) % 3 - 1, iz = cl / (nx * ny) + code / 9 - 1;
+  if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) return -1;
+  return ix + nx * (iy + ny * iz);
+}
+
+// (K Z)_(i, c') for every block row i: one thread per row, walking its SELL slice
+__global__ void k_build_kz(int64_t nslices, Grid g, const int32_t *__restrict__ slice_ptr, const int32_t *__restrict__ slot_node,
+                           const int32_t *__restrict__ colidx, const double *__restrict__ vals,
+                           const double *__restrict__ xyz, const double *__restrict__ fixdof,
+                           const int32_t *__restrict__ cid, int8_t *__restrict__ kz_rel, double *__restrict__ kz_val,
+                           int *__restrict__ err) {
+  const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t s = slot / SELL_C;
+  if (s >= nslices) return;
+  const int lane = (int)(slot % SELL_C);
+  const int32_t row = slot_node[slot];
+  if (row < 0) return;
+  const int32_t ci = cid[row];
+  int8_t codes[8];
+  double acc[8][18];
+  int used = 0;
+  for (int t = 0; t < 8; t++) {
+    codes[t] = -1;
+    for (int q = 0; q < 18; q++) acc[t][q] = 0.0;
+  }
+  for (int32_t k = slice_ptr[s]; k < slice_ptr[s + 1]; k++) {
+    const int64_t pos = (int64_t)k * SELL_C + lane;
+    const double *v = vals + (int64_t)k * 9 * SELL_C + lane;
+    double a[9];
+    bool nz = false;
+    for (int q = 0; q < 9; q++) {
+      a[q] = v[q * SELL_C];
+      nz |= a[q] != 0.0;
+    }
+    if (!nz) continue;                               // padding / eliminated block
+    const int32_t j = colidx[pos];
+    const int32_t cj = cid[j];
+    const int code = rel_code(g, ci, cj);
+    if (code < 0) { atomicExch(err, 1); continue; }
+    int t = 0;
+    while (t < used && codes[t] != code) t++;
+    if (t == used) {
+      if (used == 8) { atomicExch(err, 2); continue; }
+      codes[used++] = (int8_t)code;
+    }
+    double Z[3][6];
+    z_of(g, cj, xyz, fixdof, j, Z);
+    for (int r = 0; r < 3; r++)
+      for (int m = 0; m < 6; m++) acc[t][6 * r + m] += a[3 * r] * Z[0][m] + a[3 * r + 1] * Z[1][m] + a[3 * r + 2] * Z[2][m];
+  }
+  for (int t = 0; t < 8; t++) {
+    // slots whose block vanishes (a rigid motion of the cluster leaves an interior node force-free) are dropped
+    double mx = 0.0;
+    for (int q = 0; q < 18; q++) mx = fmax(mx, fabs(acc[t][q]));
+    kz_rel[8 * (int64_t)row + t] = (t < used && mx > 0.0) ? codes[t] : (int8_t)-1;
+    for (int q = 0; q < 18; q++) kz_val[(8 * (int64_t)row + t) * 18 + q] = acc[t][q];
+  }
+}
+
+// E(c, c') = sum over the nodes i of cluster c of Z_i^T (K Z)_(i,c'): one block per cluster, nodes in
+// list order, thread (t, entry) adds slot t's 6x6 contribution to the accumulator of its neighbour code
+__global__ void __launch_bounds__(288)
+k_build_e(Grid g, int64_t ncl, const int32_t *__restrict__ cl_ptr, const int32_t *__restrict__ cl_nodes,
+          const int8_t *__restrict__ kz_rel, const double *__restrict__ kz_val, const double *__restrict__ xyz,
+          const double *__restrict__ fixdof, double *__restrict__ E) {
+  __shared__ double acc[27][36];
+  const int c = blockIdx.x;
+  for (int q = threadIdx.x; q < 27 * 36; q += blockDim.x) (&acc[0][0])[q] = 0.0;
+  __syncthreads();
+  const int t = threadIdx.x / 36, e = threadIdx.x % 36, a = e / 6, b = e % 6;
+  for (int32_t idx = cl_ptr[c]; idx < cl_ptr[c + 1]; idx++) {
+    const int64_t i = cl_nodes[idx];
+    const int code = kz_rel[8 * i + t];
+    if (code >= 0) {
+      double Z[3][6];
+      z_of(g, c, xyz, fixdof, i, Z);
+      const double *kz = kz_val + (8 * i + t) * 18;
+      acc[code][e] += Z[0][a] * kz[b] + Z[1][a] * kz[6 + b] + Z[2][a] * kz[12 + b];
+    }
+    __syncthreads();
+  }
+  const int64_t n6 = 6 * ncl;
+  for (int q = threadIdx.x; q < 27 * 36; q += blockDim.x) {
+    const int code = q / 36, ee = q % 36;
+    const int32_t cn = neighbour(g, c, code);
+    if (cn >= 0) E[(6 * (int64_t)c + ee / 6) * n6 + 6 * (int64_t)cn + ee % 6] = acc[code][ee];
+  }
+}
+
+// E <- (E + E^T)/2 on the lower triangle, unit diagonal where a mode has no free dof
+__global__ void k_sym_guard(int64_t n, double *E) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int64_t r = idx / n, q = idx % n;
+  if (r < q) return;
+  double v = 0.5 * (E[r * n + q] + E[q * n + r]);
+  if (r == q && v == 0.0) v = 1.0;
+  E[r * n + q] = v;
+}
+__global__ void k_mirror(int64_t n, const double *__restrict__ L, double *__restrict__ F) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int64_t r = idx / n, q = idx % n;
+  // the factorisation worked on the row-major lower triangle (cuSOLVER's column-major "upper")
+  F[idx] = r >= q ? L[r * n + q] : L[q * n + r];
+}
+
+// rhs_c = sum_{i in c} w_i Z_i^T r_i  -  sum_{(i,t) -> c} (K Z)_(i,t)^T y_i        (one block per cluster)
+__global__ void __launch_bounds__(256)
+k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restrict__ cl_nodes,
+             const int32_t *__restrict__ ent_ptr, const int32_t *__restrict__ ent, const double *__restrict__ kz_val,
+             const double *__restrict__ xyz, const double *__restrict__ fixdof, const double *__restrict__ wt,
+             const double *__restrict__ r, const double *__restrict__ y, double *__restrict__ rhs,
+             const double *__restrict__ sc, int done_slot) {
+  if (sc && sc[done_slot] >= 0.0) return;
+  const int c = blockIdx.x;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  for (int32_t idx = cl_ptr[c] + threadIdx.x; idx < cl_ptr[c + 1]; idx += 256) {
+    const int64_t i = cl_nodes[idx];
+    double Z[3][6];
+    z_of(g, c, xyz, fixdof, i, Z);
+    const double w = wt ? wt[3 * i] : 1.0;
+    const double r0 = w * r[3 * i], r1 = w * r[3 * i + 1], r2 = w * r[3 * i + 2];
+#pragma unroll
+    for (int m = 0; m < 6; m++) v[m] += Z[0][m] * r0 + Z[1][m] * r1 + Z[2][m] * r2;
+  }
+  if (y) {
+    for (int32_t idx = ent_ptr[c] + threadIdx.x; idx < ent_ptr[c + 1]; idx += 256) {
+      const int64_t it = ent[idx];
+      const int64_t i = it >> 3;
+      const double *kz = kz_val + it * 18;
+      const double y0 = y[3 * i], y1 = y[3 * i + 1], y2 = y[3 * i + 2];
+#pragma unroll
+      for (int m = 0; m < 6; m++) v[m] -= kz[m] * y0 + kz[6 + m] * y1 + kz[12 + m] * y2;
+    }
+  }
+  __shared__ double sm[6][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int m = 0; m < 6; m++) {
+    const double s = warp_sum(v[m]);
+    if (lane == 0) sm[m][warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += sm[threadIdx.x][w];
+    rhs[6 * (int64_t)c + threadIdx.x] = s;
+  }
+}
+
+// lam = Einv rhs: one warp per row, fixed order
+__global__ void __launch_bounds__(256)
+k_gemv(int64_t n, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
+       const double *__restrict__ sc, int done_slot) {
+  if (sc && sc[done_slot] >= 0.0) return;
+  const int64_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (int64_t q = lane; q < n; q += 32) s += A[row * n + q] * x[q];
+  s = warp_sum(s);
+  if (lane == 0) y[row] = s;
+}
+
+// out_i = (base ? base_i : 0) + Z_i lam_(cluster of i)
+__global__ void k_expand(int64_t nn, Grid g, const int32_t *__restrict__ cid, const double *__restrict__ xyz,
+                         const double *__restrict__ fixdof, const double *__restrict__ lam,
+                         const double *__restrict__ base, double *__restrict__ out, const double *__restrict__ sc,
+                         int done_slot) {
+  if (sc && sc[done_slot] >= 0.0) return;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  const int32_t c = cid[i];
+  double Z[3][6];
+  z_of(g, c, xyz, fixdof, i, Z);
+  const double *l = lam + 6 * (int64_t)c;
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    double s = base ? base[3 * i + r] : 0.0;
+#pragma unroll
+    for (int m = 0; m < 6; m++) s += Z[r][m] * l[m];
+    out[3 * i + r] = s;
+  }
+}
+
+Grid grid_of(const fcvm_ctx *c) {
+  Grid g;
+  for (int d = 0; d < 3; d++) {
+    g.n[d] = c->dn[d];
+    g.lo[d] = c->dlo[d];
+    g.h[d] = c->dh[d];
+  }
+  g.scale = c->dscale;
+  return g;
+}
+
+template <typename T>
+int dalloc2(T **p, int64_t n) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  FCVM_CUDA(cudaMalloc((void **)p, sizeof(T) * (size_t)std::max<int64_t>(n, 1)));
+  return FCVM_OK;
+}
+
+}  // namespace
+
+extern "C" int fcvm_set_deflation(fcvm_ctx *c, int ncx, int ncy, int ncz, const int32_t *cid, const double *lo,
+                                  const double *h) {
+  FCVM_CHECK(c && c->nn > 0, FCVM_E_ARG, "fcvm_set_deflation: call fcvm_set_mesh first");
+  c->defl_ready = c->defl_structure = false;
+  if (ncx <= 0 || ncy <= 0 || ncz <= 0 || !cid) {          // switch off
+    c->dn[0] = c->dn[1] = c->dn[2] = 0;
+    c->ncl = 0;
+    return FCVM_OK;
+  }
+  FCVM_CHECK(lo && h && h[0] > 0 && h[1] > 0 && h[2] > 0, FCVM_E_ARG, "fcvm_set_deflation: bad grid");
+  const int64_t ncl = (int64_t)ncx * ncy * ncz, nn = c->nn;
+  FCVM_CHECK(6 * ncl <= 16384, FCVM_E_ARG, "fcvm_set_deflation: %lld clusters make a coarse matrix beyond 16384 unknowns",
+             (long long)ncl);
+  c->dn[0] = ncx; c->dn[1] = ncy; c->dn[2] = ncz;
+  c->ncl = ncl;
+  for (int d = 0; d < 3; d++) { c->dlo[d] = lo[d]; c->dh[d] = h[d]; }
+  c->dscale = std::max(h[0], std::max(h[1], h[2]));
+  std::vector<int32_t> ptr((size_t)ncl + 1, 0), nodes((size_t)nn);
+  for (int64_t i = 0; i < nn; i++) {
+    FCVM_CHECK(cid[i] >= 0 && cid[i] < ncl, FCVM_E_ARG, "fcvm_set_deflation: cluster of node %lld out of range", (long long)i);
+    ptr[(size_t)cid[i] + 1]++;
+  }
+  for (int64_t k = 0; k < ncl; k++) ptr[(size_t)k + 1] += ptr[(size_t)k];
+  {
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t i = 0; i < nn; i++) nodes[(size_t)fill[(size_t)cid[i]]++] = (int32_t)i;
+  }
+  FCVM_TRY(dalloc2(&c->d_cid, nn)); FCVM_TRY(dalloc2(&c->cl_ptr, ncl + 1)); FCVM_TRY(dalloc2(&c->cl_nodes, nn));
+  FCVM_CUDA(cudaMemcpy(c->d_cid, cid, sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
+  FCVM_CUDA(cudaMemcpy(c->cl_ptr, ptr.data(), sizeof(int32_t) * (ncl + 1), cudaMemcpyHostToDevice));
+  FCVM_CUDA(cudaMemcpy(c->cl_nodes, nodes.data(), sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
+  FCVM_TRY(dalloc2(&c->kz_rel, 8 * nn)); FCVM_TRY(dalloc2(&c->kz_val, 8 * 18 * nn));
+  FCVM_TRY(dalloc2(&c->dE, 36 * ncl * ncl)); FCVM_TRY(dalloc2(&c->dEinv, 36 * ncl * ncl));
+  FCVM_TRY(dalloc2(&c->d_rhs, 6 * ncl)); FCVM_TRY(dalloc2(&c->d_lam, 6 * ncl));
+  FCVM_TRY(dalloc2(&c->spmv_part2, c->nslices + 8));
+  FCVM_CUDA(cudaMemset(c->spmv_part2, 0, sizeof(double) * (c->nslices + 8)));
+  return FCVM_OK;
+}
+
+namespace fcvm {
+
+// K Z, E = Z^T K Z and its inverse for the matrix now in the context (called at the end of fcvm_assemble)
+int deflation_build(fcvm_ctx *c) {
+  c->defl_ready = false;
+  if (c->ncl == 0) return FCVM_OK;
+  cudaStream_t st = c->stream;
+  const Grid g = grid_of(c);
+  const int64_t nn = c->nn, ncl = c->ncl, n6 = 6 * ncl;
+  const double *fixdof = (const double *)c->buf[FCVM_BUF_FIXDOF];
+  int *derr;
+  FCVM_CUDA(cudaMalloc((void **)&derr, sizeof(int)));
+  FCVM_CUDA(cudaMemsetAsync(derr, 0, sizeof(int), st));
+  k_build_kz<<<grid_for(c->nslices * SELL_C, 128), 128, 0, st>>>(c->nslices, g, c->slice_ptr, c->slot_node, c->colidx,
+                                                                c->vals, c->xyz, fixdof, c->d_cid, c->kz_rel, c->kz_val,
+                                                                derr);
+  int herr = 0;
+  FCVM_CUDA(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FCVM_CUDA(cudaStreamSynchronize(st));
+  cudaFree(derr);
+  FCVM_CHECK(herr == 0, FCVM_E_ARG,
+             "deflation: a node couples to %s -- the clusters must be at least one element wide in every direction",
+             herr == 1 ? "a cluster that is not a neighbour of its own" : "more than eight clusters");
+  if (!c->defl_structure) {
+    // per target cluster: the (node, slot) entries that point to it, ascending (fixed reduction order)
+    std::vector<int8_t> rel((size_t)8 * nn);
+    std::vector<int32_t> cid((size_t)nn);
+    FCVM_CUDA(cudaMemcpy(rel.data(), c->kz_rel, (size_t)8 * nn, cudaMemcpyDeviceToHost));
+    FCVM_CUDA(cudaMemcpy(cid.data(), c->d_cid, sizeof(int32_t) * nn, cudaMemcpyDeviceToHost));
+    const int nx = c->dn[0], ny = c->dn[1];
+    auto target = [&](int32_t from, int code) {
+      return (from % nx + code % 3 - 1) + nx * (((from / nx) % ny + (code / 3) % 3 - 1) + ny * (from / (nx * ny) + code / 9 - 1));
+    };
+    std::vector<int32_t> ptr((size_t)ncl + 1, 0);
+    for (int64_t it = 0; it < 8 * nn; it++)
+      if (rel[(size_t)it] >= 0) ptr[(size_t)target(cid[(size_t)(it >> 3)], rel[(size_t)it]) + 1]++;
+    for (int64_t k = 0; k < ncl; k++) ptr[(size_t)k + 1] += ptr[(size_t)k];
+    std::vector<int32_t> ent((size_t)std::max<int32_t>(ptr[(size_t)ncl], 1)), fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t it = 0; it < 8 * nn; it++)
+      if (rel[(size_t)it] >= 0) ent[(size_t)fill[(size_t)target(cid[(size_t)(it >> 3)], rel[(size_t)it])]++] = (int32_t)it;
+    FCVM_TRY(dalloc2(&c->ent_ptr, ncl + 1)); FCVM_TRY(dalloc2(&c->ent, (int64_t)ent.size()));
+    FCVM_CUDA(cudaMemcpy(c->ent_ptr, ptr.data(), sizeof(int32_t) * (ncl + 1), cudaMemcpyHostToDevice));
+    FCVM_CUDA(cudaMemcpy(c->ent, ent.data(), sizeof(int32_t) * ent.size(), cudaMemcpyHostToDevice));
+    c->defl_structure = true;
+  }
+  FCVM_CUDA(cudaMemsetAsync(c->dE, 0, sizeof(double) * n6 * n6, st));
+  k_build_e<<<(unsigned)ncl, 288, 0, st>>>(g, ncl, c->cl_ptr, c->cl_nodes, c->kz_rel, c->kz_val, c->xyz, fixdof, c->dE);
+  if (c->world > 1) FCVM_TRY(fcvm_comm_allreduce_sum(c, c->dE, n6 * n6));
+  k_sym_guard<<<grid_for(n6 * n6, 256), 256, 0, st>>>(n6, c->dE);
+  FCVM_CUDA(cudaGetLastError());
+  // dense inverse (cuSOLVER Cholesky; column-major view of the symmetric matrix: "upper" = our lower triangle)
+  cusolverDnHandle_t h = (cusolverDnHandle_t)c->cusolver;
+  if (!h) {
+    FCVM_CHECK(cusolverDnCreate(&h) == CUSOLVER_STATUS_SUCCESS, FCVM_E_CUDA, "cusolverDnCreate failed");
+    c->cusolver = (void *)h;
+    FCVM_CUDA(cudaMalloc((void **)&c->cus_info, sizeof(int)));
+  }
+  cusolverDnSetStream(h, st);
+  int lw1 = 0, lw2 = 0;
+  cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_UPPER, (int)n6, c->dE, (int)n6, &lw1);
+  cusolverDnDpotri_bufferSize(h, CUBLAS_FILL_MODE_UPPER, (int)n6, c->dE, (int)n6, &lw2);
+  const int lw = std::max(lw1, lw2);
+  if (lw > c->cus_lwork) {
+    if (c->cus_work) cudaFree(c->cus_work);
+    FCVM_CUDA(cudaMalloc((void **)&c->cus_work, sizeof(double) * (size_t)lw));
+    c->cus_lwork = lw;
+  }
+  int info = 0;
+  FCVM_CHECK(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_UPPER, (int)n6, c->dE, (int)n6, c->cus_work, lw, c->cus_info) ==
+                 CUSOLVER_STATUS_SUCCESS, FCVM_E_CUDA, "cusolverDnDpotrf failed");
+  FCVM_CUDA(cudaMemcpyAsync(&info, c->cus_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FCVM_CUDA(cudaStreamSynchronize(st));
+  FCVM_CHECK(info == 0, FCVM_E_ARG, "deflation: coarse matrix is not positive definite (potrf info %d)", info);
+  FCVM_CHECK(cusolverDnDpotri(h, CUBLAS_FILL_MODE_UPPER, (int)n6, c->dE, (int)n6, c->cus_work, lw, c->cus_info) ==
+                 CUSOLVER_STATUS_SUCCESS, FCVM_E_CUDA, "cusolverDnDpotri failed");
+  k_mirror<<<grid_for(n6 * n6, 256), 256, 0, st>>>(n6, c->dE, c->dEinv);
+  FCVM_CUDA(cudaGetLastError());
+  c->launches += 5;
+  c->defl_ready = true;
+  return FCVM_OK;
+}
+
+// lam = E^-1 (Z^T r - (K Z)^T y); out = base + Z lam.   y / base may be null.
+int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const double *base, double *out, const double *sc,
+                      int done_slot) {
+  cudaStream_t st = c->stream;
+  const Grid g = grid_of(c);
+  const double *fixdof = (const double *)c->buf[FCVM_BUF_FIXDOF];
+  const int64_t n6 = 6 * c->ncl;
+  k_coarse_rhs<<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val, c->xyz, fixdof,
+                                                c->dof_weight, r, y, c->d_rhs, sc, done_slot);
+  if (c->world > 1) FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_rhs, n6));
+  k_gemv<<<grid_for(n6, 8), 256, 0, st>>>(n6, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
+  k_expand<<<grid_for(c->nn, 256), 256, 0, st>>>(c->nn, g, c->d_cid, c->xyz, fixdof, c->d_lam, base, out, sc, done_slot);
+  c->launches += 3;
+  FCVM_CUDA(cudaGetLastError());
+  return FCVM_OK;
+}
+
+void deflation_free(fcvm_ctx *c) {
+  cudaFree(c->d_cid); cudaFree(c->cl_ptr); cudaFree(c->cl_nodes); cudaFree(c->kz_rel); cudaFree(c->kz_val);
+  cudaFree(c->ent_ptr); cudaFree(c->ent); cudaFree(c->dE); cudaFree(c->dEinv); cudaFree(c->d_rhs); cudaFree(c->d_lam);
+  cudaFree(c->spmv_part2);
+  c->d_cid = c->cl_ptr = c->cl_nodes = c->ent_ptr = c->ent = nullptr;
+  c->kz_rel = nullptr;
+  c->kz_val = c->dE = c->dEinv = c->d_rhs = c->d_lam = c->spmv_part2 = nullptr;
+  c->ncl = 0;
+  c->dn[0] = c->dn[1] = c->dn[2] = 0;
+  c->defl_ready = c->defl_structure = false;
+}
+
+}  // namespace fcvm

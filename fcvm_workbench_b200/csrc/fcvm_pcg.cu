@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(32 * SPMV_SPLIT)
 k_spmv_sell(int64_t nlist, const int32_t *__restrict__ slices, const int32_t *__restrict__ slice_ptr,
                   const int32_t *__restrict__ slot_node, const int32_t *__restrict__ colidx,
                   const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-                  const double *__restrict__ sc, int rr_slot, double *dot_part) {
+                  const double *__restrict__ sc, int rr_slot, double *dot_part, const double *__restrict__ rvec,
+                  const double *__restrict__ wt, double *dot_part2) {
   if (sc && (sc[S_ITERS] >= 0.0 || sc[rr_slot] <= sc[S_THR])) return;
   __shared__ double part[SPMV_SPLIT - 1][3][32];
   const int64_t s = slices ? slices[blockIdx.x] : (int64_t)blockIdx.x;
@@ -78,38 +79,58 @@ k_spmv_sell(int64_t nlist, const int32_t *__restrict__ slices, const int32_t *__
     y2 += part[q][2][lane];
   }
   const int32_t row = slot_node[s * SELL_C + lane];
-  double dsum = 0.0;
+  double dsum = 0.0, rsum = 0.0;
   if (row >= 0) {
     const int64_t r3 = 3 * (int64_t)row;
     y[r3] = y0;
     y[r3 + 1] = y1;
     y[r3 + 2] = y2;
     if (dot_part) dsum = y0 * x[r3] + y1 * x[r3 + 1] + y2 * x[r3 + 2];
+    if (dot_part2) rsum = (wt ? wt[r3] : 1.0) * (rvec[r3] * x[r3] + rvec[r3 + 1] * x[r3 + 1] + rvec[r3 + 2] * x[r3 + 2]);
   }
   if (dot_part) {
     dsum = warp_sum(dsum);
     if (lane == 0) dot_part[s] = dsum;
   }
+  if (dot_part2) {
+    // r.u with the deflated preconditioner (u is only complete after the coarse correction); on a
+    // partitioned mesh shared rows count once (weight 1/multiplicity)
+    rsum = warp_sum(rsum);
+    if (lane == 0) dot_part2[s] = rsum;
+  }
 }
 
-// delta = sum of the per-slice partials of w.u, in slice order (one block, fixed shape); with a
-// communicator the three per-rank sums are placed at the tail of the interface vector instead
+// delta = sum of the per-slice partials of w.u, in slice order (one block, fixed shape), and with
+// `part2` gamma = r.u likewise; with a communicator the per-rank sums go to the tail buffer of the
+// scalar all-reduce instead
 __global__ void __launch_bounds__(1024)
-k_dot_finish(int64_t n, const double *__restrict__ part, double *sc, int out_slot, double *tail) {
+k_dot_finish(int64_t n, const double *__restrict__ part, const double *__restrict__ part2, double *sc, int delta_slot,
+             int gamma_slot, double *tail) {
   if (sc[S_ITERS] >= 0.0) return;
-  double t = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += 1024) t += part[i];
-  __shared__ double sm[32];
+  double t = 0.0, g = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    t += part[i];
+    if (part2) g += part2[i];
+  }
+  __shared__ double sm[2][32];
   t = warp_sum(t);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = t;
+  g = warp_sum(g);
+  if ((threadIdx.x & 31) == 0) {
+    sm[0][threadIdx.x >> 5] = t;
+    sm[1][threadIdx.x >> 5] = g;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double tot = 0.0;
+    double tot = 0.0, gam = 0.0;
 #pragma unroll
-    for (int w = 0; w < 32; w++) tot += sm[w];
-    sc[out_slot] = tot;
+    for (int w = 0; w < 32; w++) {
+      tot += sm[0][w];
+      gam += sm[1][w];
+    }
+    sc[delta_slot] = tot;
+    if (part2 && gamma_slot >= 0) sc[gamma_slot] = gam;
     if (tail) {
-      tail[0] = sc[L_RU];
+      tail[0] = part2 ? gam : sc[L_RU];
       tail[1] = sc[L_RR];
       tail[2] = tot;
     }
@@ -159,7 +180,7 @@ __global__ void k_pcg_scalars(double rtol, double *sc) {
 //   p = u + beta p ; s = w + beta s (= K p) ; x += alpha p ; r -= alpha s ; u = M^-1 r
 // and the sums r.u (-> gamma_(it+1)) and r.r.  w = K u and delta = w.u come from the SpMV that follows.
 __global__ void __launch_bounds__(RED_THREADS)
-k_pcg_step(int64_t nn, int it, const double *__restrict__ w, const double *__restrict__ minv,
+k_pcg_step(int64_t nn, int it, int defl, const double *__restrict__ w, const double *__restrict__ minv,
            const double *__restrict__ wt_, double *x, double *r, double *u, double *p, double *s, double *red_part,
            unsigned int *counter, double *sc, Slots<2> sl) {
   const int cur = it & 1, prv = cur ^ 1;
@@ -196,7 +217,7 @@ k_pcg_step(int64_t nn, int it, const double *__restrict__ w, const double *__res
     apply_minv(minv + 9 * n, rn[0], rn[1], rn[2], z0, z1, z2);
     u[d] = z0; u[d + 1] = z1; u[d + 2] = z2;
     const double wt = wt_ ? wt_[d] : 1.0;
-    v[0] += wt * (rn[0] * z0 + rn[1] * z1 + rn[2] * z2);
+    if (!defl) v[0] += wt * (rn[0] * z0 + rn[1] * z1 + rn[2] * z2);   // deflated: r.u follows the coarse correction
     v[1] += wt * (rn[0] * rn[0] + rn[1] * rn[1] + rn[2] * rn[2]);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) sc[S_ALPHA + cur] = alpha;
@@ -206,21 +227,21 @@ k_pcg_step(int64_t nn, int it, const double *__restrict__ w, const double *__res
 // multi-GPU: the three per-rank sums ride at the tail of the interface vector (one all-reduce per iteration)
 __global__ void k_tail_get(const double *__restrict__ tail, double *sc, int gamma_slot, int rr_slot) {
   if (sc[S_ITERS] >= 0.0) return;
-  if (gamma_slot >= 0) {
-    sc[gamma_slot] = tail[0];
-    sc[rr_slot] = tail[1];
-  }
+  if (gamma_slot >= 0) sc[gamma_slot] = tail[0];
+  if (rr_slot >= 0) sc[rr_slot] = tail[1];
   sc[S_DELTA] = tail[2];
 }
 
 }  // namespace
 
 static void spmv_launch(fcvm_ctx *c, const double *x, double *y, const double *sc, int rr_slot, double *dot_part,
-                        const int32_t *list = nullptr, int64_t nlist = -1) {
+                        const int32_t *list = nullptr, int64_t nlist = -1, const double *rvec = nullptr,
+                        double *dot_part2 = nullptr) {
   const int64_t nb = list ? nlist : c->nslices;
   if (nb <= 0) return;
   k_spmv_sell<<<(unsigned)nb, 32 * SPMV_SPLIT, 0, c->stream>>>(nb, list, c->slice_ptr, c->slot_node, c->colidx,
-                                                              c->vals, x, y, sc, rr_slot, dot_part);
+                                                              c->vals, x, y, sc, rr_slot, dot_part, rvec,
+                                                              c->dof_weight, dot_part2);
 }
 
 namespace fcvm {
@@ -242,6 +263,8 @@ extern "C" int fcvm_spmv(fcvm_ctx *c, const double *x, double *y) {
 namespace fcvm {
 int interface_sum_on_comm_stream(fcvm_ctx *c, double *v);
 int comm_allreduce_on(fcvm_ctx *c, double *dev, int64_t n, cudaStream_t st);
+int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const double *base, double *out, const double *sc,
+                      int done_slot);
 }
 
 extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rtol, int max_iter, int use_x0,
@@ -258,6 +281,8 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
     FCVM_CUDA(cudaMemsetAsync(c->spmv_part, 0, sizeof(double) * (size_t)(c->nslices + 8), st));
   }
   double *r = c->pcg_r, *u = c->pcg_z, *p = c->pcg_p, *wv = c->pcg_q, *s = c->pcg_s;
+  const bool defl = c->defl_ready;
+  double *part2 = defl ? c->spmv_part2 : nullptr;
   const double *q0 = nullptr;
   if (use_x0) {
     FCVM_TRY(fcvm_spmv(c, x, wv));
@@ -265,12 +290,21 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
   } else {
     FCVM_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n3, st));
   }
-  {
+  auto init = [&]() -> int {
     ProfScope ps(c, 3);
     Slots<3> sl = multi ? Slots<3>{{L_RU, L_BB, L_RR}} : Slots<3>{{S_GAMMA, S_BB, S_RR}};
     k_pcg_init<<<RED_BLOCKS, RED_THREADS, 0, st>>>(nn, b, q0, c->minv, w, r, u, p, s, c->red_part, c->red_counter,
                                                    sc, sl);
     c->launches++;
+    return FCVM_OK;
+  };
+  FCVM_TRY(init());
+  if (defl) {
+    // start from x + Z E^-1 Z^T (b - K x): the residual of the deflated iteration is orthogonal to Z
+    FCVM_TRY(deflation_correct(c, r, nullptr, x, x, nullptr, 0));
+    FCVM_TRY(fcvm_spmv(c, x, wv));
+    q0 = wv;
+    FCVM_TRY(init());
   }
   if (multi) {
     FCVM_TRY(fcvm_comm_allreduce_oop(c, sc + L_RU, sc + S_GAMMA, 1));
@@ -279,21 +313,25 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
   }
   k_pcg_scalars<<<1, 1, 0, st>>>(rtol, sc);
   c->launches++;
-  // w = K u and delta = w.u; with a communicator the partial sums travel with the interface all-reduce
-  // w = K u and delta = w.u.  With a communicator the slices that hold interface rows are multiplied
-  // first; their exchange (pack, all-reduce, unpack) runs on the communication stream while the
-  // interior slices are multiplied, and only the three-scalar all-reduce stays on the critical path.
+  // w = K u and delta = w.u (deflated: first u = y + Z E^-1 (Z^T r - (K Z)^T y), and gamma = r.u with it).
+  // With a communicator the slices that hold interface rows are multiplied first; their exchange (pack,
+  // all-reduce, unpack) runs on the communication stream while the interior slices are multiplied, and
+  // only the three-scalar all-reduce stays on the critical path.
   auto spmv_dot = [&](int it_next) -> int {
     const int flag = S_RR + ((it_next + (multi ? 1 : 0)) & 1);
     // early-out test: r.r of the newest iterate whose global value is known -- the one this product
     // belongs to on one GPU; with a communicator that sum is still in flight, so the one before
+    if (defl) {
+      ProfScope ps(c, 3);
+      FCVM_TRY(deflation_correct(c, r, u, u, u, sc, S_ITERS));
+    }
     if (!multi) {
       ProfScope ps(c, 0);
-      spmv_launch(c, u, wv, sc, flag, c->spmv_part);
+      spmv_launch(c, u, wv, sc, flag, c->spmv_part, nullptr, -1, r, part2);
     } else {
       {
         ProfScope ps(c, 0);
-        spmv_launch(c, u, wv, sc, flag, c->spmv_part, c->bslices, c->n_bslices);
+        spmv_launch(c, u, wv, sc, flag, c->spmv_part, c->bslices, c->n_bslices, r, part2);
       }
       FCVM_CUDA(cudaEventRecord(c->ev_boundary, st));
       FCVM_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_boundary, 0));
@@ -301,20 +339,23 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
       FCVM_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
       {
         ProfScope ps(c, 0);
-        spmv_launch(c, u, wv, sc, flag, c->spmv_part, c->islices, c->n_islices);
+        spmv_launch(c, u, wv, sc, flag, c->spmv_part, c->islices, c->n_islices, r, part2);
       }
       c->launches++;
     }
     {
       ProfScope ps(c, 3);
-      k_dot_finish<<<1, 1024, 0, st>>>(c->nslices, c->spmv_part, sc, multi ? L_WU : S_DELTA, multi ? c->tail3 : nullptr);
+      k_dot_finish<<<1, 1024, 0, st>>>(c->nslices, c->spmv_part, part2, sc, multi ? L_WU : S_DELTA,
+                                       multi ? -1 : S_GAMMA + (it_next & 1), multi ? c->tail3 : nullptr);
     }
     c->launches += 2;
     if (multi) {
       FCVM_TRY(comm_allreduce_on(c, c->tail3, 3, st));
       FCVM_CUDA(cudaStreamWaitEvent(st, c->ev_halo, 0));
-      // gamma / rr of the iterate that the next vector step will test; the first call only brings delta
-      k_tail_get<<<1, 1, 0, st>>>(c->tail3, sc, it_next > 0 ? S_GAMMA + (it_next & 1) : -1, S_RR + (it_next & 1));
+      // gamma / rr of the iterate that the next vector step will test; the first call brings delta (and,
+      // deflated, gamma) only: rr of the start vector is already global
+      k_tail_get<<<1, 1, 0, st>>>(c->tail3, sc, (it_next > 0 || defl) ? S_GAMMA + (it_next & 1) : -1,
+                                  it_next > 0 ? S_RR + (it_next & 1) : -1);
       c->launches++;
     }
     return FCVM_OK;
@@ -327,8 +368,9 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
       {
         ProfScope ps(c, 3);
         const int nxt = (it + 1) & 1;
-        Slots<2> sl = multi ? Slots<2>{{L_RU, L_RR}} : Slots<2>{{S_GAMMA + nxt, S_RR + nxt}};
-        k_pcg_step<<<RED_BLOCKS, RED_THREADS, 0, st>>>(nn, it, wv, c->minv, w, x, r, u, p, s, c->red_part,
+        // deflated: the vector step's own r.u is void (slot L_RU as a sink), gamma comes with the product
+        Slots<2> sl = multi ? Slots<2>{{L_RU, L_RR}} : Slots<2>{{defl ? L_RU : S_GAMMA + nxt, S_RR + nxt}};
+        k_pcg_step<<<RED_BLOCKS, RED_THREADS, 0, st>>>(nn, it, defl ? 1 : 0, wv, c->minv, w, x, r, u, p, s, c->red_part,
                                                        c->red_counter, sc, sl);
         c->launches++;
       }

@@ -12,6 +12,7 @@
 using namespace fcvm;
 
 namespace fcvm {
+int deflation_build(fcvm_ctx *c);
 int launch_node_gather(fcvm_ctx *c, double *out, int accumulate);
 int launch_spmv(fcvm_ctx *c, const double *x, double *y);
 }  // namespace fcvm
@@ -414,7 +415,7 @@ extern "C" int fcvm_assemble(fcvm_ctx *c, int tangent, const double *disp, doubl
   k_block_inverse<<<grid_for(c->nn, 128), 128, 0, c->stream>>>(c->nn, c->diag9, c->minv);
   c->launches += 4;
   FCVM_CUDA(cudaGetLastError());
-  return FCVM_OK;
+  return deflation_build(c);       // K Z and (Z^T K Z)^-1 of the second preconditioner level, when switched on
 }
 
 extern "C" int fcvm_element_matrices(fcvm_ctx *c, int tangent, const double *disp, double Et_E, double *esm_dev) {

@@ -60,6 +60,8 @@ class Engine:
         mat = np.asarray(materialbyElement, dtype=np.float64)
         self.ne, self.nn = int(el.shape[0]), int(xyz.shape[0])
         self.ndof = 3 * self.nn
+        self._elNodes, self._nocoord = el, xyz
+        self.deflation_grid = None
         self.E, self.nu, self.density = float(mat[0][0]), float(mat[0][1]), float(mat[0][2])
         call("fcvm_set_mesh", self._ctx, self.ne, self.nn, _ptr(el, i64p), _ptr(xyz, f64p), self.E, self.nu,
              self.density)
@@ -104,6 +106,42 @@ class Engine:
                 val[int(d)] = float(v)
         self.fixmask, self.fixval = mask, val
         call("fcvm_set_constraints", self._ctx, _ptr(mask, u8p), _ptr(val, f64p))
+
+    def set_deflation(self, target_unknowns: int = 3072, grid=None):
+        """Switch on the second preconditioner level: rigid-body-mode deflation over box clusters of
+        nodes (csrc/fcvm_deflation.cu).  ``target_unknowns`` bounds the dense coarse problem (six per
+        cluster); ``grid=(ncx, ncy, ncz)`` overrides the automatic choice; ``target_unknowns=0``
+        switches it off.  Takes effect at the next ``assemble``.  Returns the grid used."""
+        if not target_unknowns and grid is None:
+            call("fcvm_set_deflation", self._ctx, 0, 0, 0, None, None, None)
+            self.deflation_grid = None
+            return None
+        xyz, el = self._nocoord, self._elNodes
+        lo, hi = xyz.min(axis=0), xyz.max(axis=0)
+        ext = np.ptp(xyz[el - 1], axis=1).max(axis=0)                 # widest element per direction
+        if self.comm is not None and self.comm.world > 1:
+            every = self.comm.allgather((lo, hi, ext))
+            lo = np.min([e[0] for e in every], axis=0)
+            hi = np.max([e[1] for e in every], axis=0)
+            ext = np.max([e[2] for e in every], axis=0)
+        size = np.maximum(hi - lo, 1e-300)
+        if grid is None:
+            m = max(1, int(target_unknowns) // 6)
+            h0 = (float(np.prod(size)) / m) ** (1.0 / 3.0)
+            grid = np.maximum(1, np.round(size / h0).astype(int))
+        grid = np.asarray(grid, dtype=int)
+        # a box at least one element wide: a node then couples to at most 2 x 2 x 2 boxes
+        grid = np.maximum(1, np.minimum(grid, np.floor(size / np.maximum(1.0001 * ext, 1e-300)).astype(int)))
+        while 6 * int(np.prod(grid)) > 16384:
+            grid[int(np.argmax(grid))] -= 1
+        h = size / grid
+        ijk = np.minimum(((xyz - lo) / h).astype(np.int64), grid - 1)
+        cid = np.ascontiguousarray(ijk[:, 0] + grid[0] * (ijk[:, 1] + grid[1] * ijk[:, 2]), dtype=np.int32)
+        lo_c, h_c = _np(lo, np.float64), _np(h, np.float64)
+        call("fcvm_set_deflation", self._ctx, int(grid[0]), int(grid[1]), int(grid[2]),
+             cid.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _ptr(lo_c, f64p), _ptr(h_c, f64p))
+        self.deflation_grid = tuple(int(g) for g in grid)
+        return self.deflation_grid
 
     # -- device vectors ---------------------------------------------------------------------
     def vec(self, n: Optional[int] = None, host=None) -> int:
@@ -219,8 +257,17 @@ class Engine:
         ``glv`` (device, holding the surface loads) receives the gravity load; ``modf`` is left
         in the named buffer MODF.
         """
-        call("fcvm_assemble", self._ctx, 1 if tangent else 0, ctypes.c_void_p(disp) if disp else None, float(Et_E),
-             float(grav[0]), float(grav[1]), float(grav[2]), ctypes.c_void_p(glv) if glv else None)
+        try:
+            call("fcvm_assemble", self._ctx, 1 if tangent else 0, ctypes.c_void_p(disp) if disp else None, float(Et_E),
+                 float(grav[0]), float(grav[1]), float(grav[2]), ctypes.c_void_p(glv) if glv else None)
+        except FcvmError as e:
+            if "deflation" not in str(e):
+                raise
+            # the matrix itself is assembled; only the coarse level could not be built (e.g. a box with
+            # fewer free dofs than rigid-body modes): carry on with block-Jacobi PCG alone
+            import warnings
+            warnings.warn(f"deflation switched off: {e}")
+            self.set_deflation(0)
         if glv and self.comm is not None and self.comm.world > 1:
             self.interface_sum(glv)
 
@@ -459,7 +506,7 @@ def mapStresses(averaged, elNodes, nocoord, sig, peeq, sigvm, csr, noce, sig_yie
 # calcDisp: the load-stepping driver (fcVM.py:1083-1635), vectors resident on the device.
 # ----------------------------------------------------------------------------------------------
 def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=None, engine: Optional[Engine] = None,
-             comm=None, on_iteration=None):
+             comm=None, on_iteration=None, deflation: Optional[int] = None):
     """Run the whole load-displacement analysis on the GPU.
 
     Same control flow as the reference (arc-length corrected modified Newton with restarts,
@@ -473,6 +520,8 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
     eng = engine or Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix, device=device, comm=comm)
     if not own:
         eng.set_constraints(m.fix)
+    if deflation is not None and hasattr(eng, "set_deflation"):
+        eng.set_deflation(deflation)
     ndof, nelem = eng.ndof, eng.ne
     nstep, iterat_max, error_max = ctl.nstep, ctl.iterat_max, ctl.error_max
     relax, scale_re, scale_up, scale_dn = ctl.relax, ctl.scale_re, ctl.scale_up, ctl.scale_dn

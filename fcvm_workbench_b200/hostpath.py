@@ -82,6 +82,9 @@ class HostEngine:
         self._nodal[_fc.FIXDOF][:] = 1.0 - self.dev.fixmask
         self._movdof[:] = (self.dev.fixmask != 0) & (self.dev.fixval != 0.0)
 
+    def set_deflation(self, *a, **k):
+        return self.dev.set_deflation(*a, **k)
+
     def set_constraints(self, fix):
         self.dev.set_constraints(fix)
         self._set_masks()

@@ -141,6 +141,14 @@ int fcvm_spmv(fcvm_ctx *ctx, const double *x, double *y);
 int fcvm_pcg_solve(fcvm_ctx *ctx, const double *b, double *x, double rtol, int max_iter, int use_x0, int *iters,
                    double *relres);
 
+/* Second preconditioner level (optional): deflation of the rigid-body modes of box clusters of nodes.
+ * The clusters form an ncx x ncy x ncz grid of boxes lo + (i,j,k)*h over the (global) bounding box;
+ * cid[n] = ix + ncx*(iy + ncy*iz) is the box of local node n.  A box must be at least one element
+ * wide in every direction.  Takes effect at the next fcvm_assemble (K Z and (Z^T K Z)^-1 are built
+ * there); ncx = 0 switches it off.  6*ncx*ncy*ncz <= 16384. */
+int fcvm_set_deflation(fcvm_ctx *ctx, int ncx, int ncy, int ncz, const int32_t *cid, const double *lo,
+                       const double *h);
+
 /* ---- stress update: update_stress_load (fcVM.py:2196-2464) ---------------------------------- */
 /* Reads SIG_OLD / SIG_YIELD, writes SIG_NEW / SIG_TEST / PGP, and qin = internal force vector
  * (overwritten, not accumulated: the reference always passes zeros, fcVM.py:1324, 1441).
