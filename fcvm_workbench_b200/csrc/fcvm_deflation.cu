@@ -9,7 +9,7 @@
 // and the start vector x0 + Z E^-1 Z^T (b - K x0); the iteration count then scales with the cluster
 // size H/h instead of the domain size L/h.  Everything is deterministic: fixed lists, fixed-shape
 // reductions, no floating-point atomics.  K Z is stored sparsely per node (a node couples to at most
-// 2 x 2 x 2 clusters because a cluster is at least one element wide).
+// 2 x 2 x 2 clusters because a cluster is at least two elements wide).
 #include <cusolverDn.h>
 
 #include <algorithm>
@@ -319,7 +319,7 @@ int deflation_build(fcvm_ctx *c) {
   FCVM_CUDA(cudaStreamSynchronize(st));
   cudaFree(derr);
   FCVM_CHECK(herr == 0, FCVM_E_ARG,
-             "deflation: a node couples to %s -- the clusters must be at least one element wide in every direction",
+             "deflation: a node couples to %s -- the clusters must be at least two elements wide in every direction",
              herr == 1 ? "a cluster that is not a neighbour of its own" : "more than eight clusters");
   if (!c->defl_structure) {
     // per target cluster: the (node, slot) entries that point to it, ascending (fixed reduction order)

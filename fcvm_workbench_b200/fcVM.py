@@ -22,6 +22,7 @@ fallback: without the library or a CUDA device the calls raise ``FcvmError``.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import numpy as np
@@ -71,6 +72,8 @@ class Engine:
             comm.attach(self)
         if fix is not None:
             self.set_constraints(fix)
+        if os.environ.get("FCVM_DEFLATION"):                      # e.g. FCVM_DEFLATION=6144 (coarse unknowns)
+            self.set_deflation(int(os.environ["FCVM_DEFLATION"]))
 
     # -- lifetime ------------------------------------------------------------------------
     def close(self):
@@ -130,8 +133,9 @@ class Engine:
             h0 = (float(np.prod(size)) / m) ** (1.0 / 3.0)
             grid = np.maximum(1, np.round(size / h0).astype(int))
         grid = np.asarray(grid, dtype=int)
-        # a box at least one element wide: a node then couples to at most 2 x 2 x 2 boxes
-        grid = np.maximum(1, np.minimum(grid, np.floor(size / np.maximum(1.0001 * ext, 1e-300)).astype(int)))
+        # a box at least two elements wide: the nodes a node couples to lie within one element either
+        # side of it, i.e. in at most 2 x 2 x 2 boxes
+        grid = np.maximum(1, np.minimum(grid, np.floor(size / np.maximum(2.0001 * ext, 1e-300)).astype(int)))
         while 6 * int(np.prod(grid)) > 16384:
             grid[int(np.argmax(grid))] -= 1
         h = size / grid

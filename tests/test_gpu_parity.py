@@ -323,7 +323,7 @@ def test_bench_workload_at_bench_tolerance_vs_oracle(fc, oracle):
     import bench
     m, c = bench.workload(5)
     ref = oracle.calcDisp(m, c)
-    o = fc.calcDisp(m, c, rtol=1e-8)
+    o = fc.calcDisp(m, c, rtol=1e-8, deflation=bench.DEFLATION)
     assert list(o["iters"]) == list(ref["iters"])
     assert sum(o["iters"]) > 20
     for k in ("lout", "un", "peeqplot"):
@@ -422,3 +422,29 @@ def test_zero_right_hand_side_and_fully_fixed_model(fc):
         indptr, indices, data = eng.export_csc_lower()
         assert len(indices) == 3 * m.nn and np.array_equal(indices, np.arange(3 * m.nn))     # diagonal only
         assert np.array_equal(data, np.repeat(m.noce.astype(float), 3))                        # = elements per node
+
+
+def test_deflated_pcg_matches_block_jacobi_and_cuts_iterations(fc):
+    """Second preconditioner level (rigid-body-mode deflation): same solution to the tolerance, far fewer
+    iterations, bit-reproducible, true residual meets the tolerance."""
+    import bench
+    m, _ = bench.workload(10)
+    res = {}
+    for tgt in (0, 6 * 27):
+        with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+            grid = eng.set_deflation(tgt)
+            glv = eng.vec()
+            eng.assemble(glv)
+            f, zero, x, x2, y = eng.vec(), eng.vec(), eng.vec(), eng.vec(), eng.vec()
+            eng.residual(1.0, glv, zero, f)
+            eng.axpby(1.0, eng.buf(fc.MODF), 1.0, f)
+            its, rr = eng.solve(f, x, 1e-10)
+            its2, _ = eng.solve(f, x2, 1e-10)
+            eng.spmv(x, y)
+            eng.axpby(1.0, f, -1.0, y)
+            res[tgt] = (grid, its, eng.get(x), eng.norm(y) / eng.norm(f))
+            assert its2 == its and np.array_equal(eng.get(x), eng.get(x2))
+    assert res[0][0] is None and res[162][0] == (3, 3, 3)
+    assert res[162][3] <= 1.01e-10 and res[0][3] <= 1.01e-10
+    assert res[162][1] < 0.6 * res[0][1]
+    assert rel(res[162][2], res[0][2]) < 1e-8
