@@ -17,6 +17,7 @@ from fcvm_workbench_b200 import fcVM, partition
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 55
 rtol = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-8
+deflation = int(sys.argv[3]) if len(sys.argv) > 3 else bench.DEFLATION
 rank, world, local = bench.dist_env()
 torch.cuda.set_device(local)
 comm = None
@@ -35,18 +36,18 @@ t0 = time.time()
 eng = fcVM.Engine(lm.elNodes, lm.nocoord, lm.materialbyElement, lm.fix, device=local, comm=comm)
 eng.synchronize()
 t1 = time.time()
-out = fcVM.calcDisp(lm, ctl, engine=eng, rtol=rtol, max_iter=200000)
+out = fcVM.calcDisp(lm, ctl, engine=eng, rtol=rtol, max_iter=200000, deflation=deflation)
 eng.synchronize()
 t2 = time.time()
 if rank == 0:
-    res = dict(n=n, elements=m.ne, nodes=m.nn, world=world, rtol=rtol, setup_s=t1 - t0, analysis_s=t2 - t1,
+    res = dict(n=n, elements=m.ne, nodes=m.nn, world=world, rtol=rtol, deflation_grid=eng.deflation_grid, setup_s=t1 - t0, analysis_s=t2 - t1,
                newton_iterations=int(out["iterat_tot"]), iters=[int(i) for i in out["iters"]],
                pcg_iterations=int(np.sum(out["pcg_iterations"])), lout=[float(v) for v in out["lout"]],
                un=[float(v) for v in out["un"]], lbd=[float(v) for v in out["lbd"]],
                peeqplot=[float(v) for v in out["peeqplot"]], csrplot=[float(v) for v in out["csrplot"]],
                nplastic=[int(v) for v in out["nplastic"]], launches=int(out["launches"]))
     os.makedirs("gpurun_out", exist_ok=True)
-    with open(f"gpurun_out/collapse_n{n}_N{world}.json", "w") as f:
+    with open(f"gpurun_out/collapse_n{n}_N{world}_d{deflation}.json", "w") as f:
         json.dump(res, f)
     print(f"n={n} N={world}: {m.ne} elements, {len(res['iters'])} load steps, {res['newton_iterations']} Newton iterations, "
           f"{res['pcg_iterations']} PCG iterations, analysis {res['analysis_s']:.1f} s (setup {res['setup_s']:.1f} s); "

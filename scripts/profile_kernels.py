@@ -11,6 +11,8 @@ from fcvm_workbench_b200 import fcVM
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 55
 m, c = bench.workload(n)
 eng = fcVM.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix)
+if os.environ.get('PROFILE_DEFLATION'):
+    eng.set_deflation(int(os.environ['PROFILE_DEFLATION']))
 glv = eng.vec()
 eng.assemble(glv)                                    # k_elem_stiffness, k_coo_reduce, k_apply_constraints, ...
 rng = np.random.default_rng(0)
