@@ -120,6 +120,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(kernel, n, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of the same
+    kernel at the same size (profiles/traffic.json); None when there is no capture of this configuration."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f).get(kernel)
+    except (OSError, ValueError):
+        return None
+    if t and t.get("n") == n and t.get("n_gpus") == world:
+        return int(t["dram_bytes_per_launch"])
+    return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -361,7 +375,8 @@ def main():
             "e2e": e2e,
             "roofline": {"kernel": "k_spmv_sell (block-SELL SpMV inside PCG, 4 warps per 32-row slice)", "bound": "hbm",
                          "achieved": spmv.get("achieved_gbs"), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": spmv.get("frac_of_hbm_peak"), "traffic": None, "peak_source": peak_src,
+                         "frac": spmv.get("frac_of_hbm_peak"), "traffic": measured_traffic("k_spmv_sell", a.n, world),
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": spmv.get("algorithmic_bytes"),
                          "avg_launch_ms": spmv.get("avg_ms_per_product", spmv.get("avg_ms"))},
             "kernels": kern,

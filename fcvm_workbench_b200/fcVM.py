@@ -127,18 +127,7 @@ class Engine:
             lo = np.min([e[0] for e in every], axis=0)
             hi = np.max([e[1] for e in every], axis=0)
             ext = np.max([e[2] for e in every], axis=0)
-        size = np.maximum(hi - lo, 1e-300)
-        if grid is None:
-            m = max(1, int(target_unknowns) // 6)
-            h0 = (float(np.prod(size)) / m) ** (1.0 / 3.0)
-            grid = np.maximum(1, np.round(size / h0).astype(int))
-        grid = np.asarray(grid, dtype=int)
-        # a box at least two elements wide: the nodes a node couples to lie within one element either
-        # side of it, i.e. in at most 2 x 2 x 2 boxes
-        grid = np.maximum(1, np.minimum(grid, np.floor(size / np.maximum(2.0001 * ext, 1e-300)).astype(int)))
-        while 6 * int(np.prod(grid)) > 16384:
-            grid[int(np.argmax(grid))] -= 1
-        h = size / grid
+        grid, h = deflation_boxes(lo, hi, ext, target_unknowns, grid)
         ijk = np.minimum(((xyz - lo) / h).astype(np.int64), grid - 1)
         cid = np.ascontiguousarray(ijk[:, 0] + grid[0] * (ijk[:, 1] + grid[1] * ijk[:, 2]), dtype=np.int32)
         lo_c, h_c = _np(lo, np.float64), _np(h, np.float64)
@@ -402,6 +391,25 @@ class Engine:
         self.pcg_iterations = getattr(self, "pcg_iterations", 0) + it.value
         self.pcg_solves = getattr(self, "pcg_solves", 0) + 1
         return x
+
+
+def deflation_boxes(lo, hi, elem_extent, target_unknowns=3072, grid=None):
+    """Box grid of the deflation level: about ``target_unknowns / 6`` near-cubic boxes over the bounding
+    box ``lo..hi``, every box at least two elements wide (``elem_extent`` = widest element per direction:
+    the nodes a node couples to then lie in at most 2 x 2 x 2 boxes) and at most 16384 coarse unknowns.
+    Returns (boxes per direction, box size)."""
+    lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+    size = np.maximum(hi - lo, 1e-300)
+    if grid is None:
+        m = max(1, int(target_unknowns) // 6)
+        h0 = (float(np.prod(size)) / m) ** (1.0 / 3.0)
+        grid = np.maximum(1, np.round(size / h0).astype(int))
+    grid = np.asarray(grid, dtype=int).copy()
+    widest = np.floor(size / np.maximum(2.0001 * np.asarray(elem_extent, dtype=np.float64), 1e-300)).astype(int)
+    grid = np.maximum(1, np.minimum(grid, widest))
+    while 6 * int(np.prod(grid)) > 16384:
+        grid[int(np.argmax(grid))] -= 1
+    return grid, size / grid
 
 
 # ----------------------------------------------------------------------------------------------

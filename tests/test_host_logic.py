@@ -106,3 +106,24 @@ def test_plate_with_hole_mesh_is_valid_and_curved():
     r = np.hypot(m.nocoord[:, 0], m.nocoord[:, 1])
     assert abs(r.min() - 10.0) < 1e-9 and m.nocoord[:, 0].max() == pytest.approx(50.0)
     assert m.movdof.sum() > 0 and len(m.fix) > 0
+
+
+def test_deflation_box_grid():
+    from fcvm_workbench_b200.fcVM import deflation_boxes
+    # 1M-element cube of the bench: 55 cells of 10/55 per edge -> 10 x 10 x 10 boxes for 6144 unknowns
+    g, h = deflation_boxes([0, 0, 0], [10, 10, 10], [10 / 55] * 3, 6144)
+    assert tuple(g) == (10, 10, 10) and np.allclose(h, 1.0)
+    # a slab: boxes stay near-cubic
+    g, h = deflation_boxes([0, 0, 0], [10, 10, 80], [0.2, 0.2, 0.2], 6 * 512)
+    assert g[2] > 4 * g[0] and abs(np.prod(g) - 512) < 200
+    # coarse meshes: never narrower than two elements, so tiny meshes end with a single box
+    g, _ = deflation_boxes([0, 0, 0], [4, 4, 4], [2, 2, 2], 6144)
+    assert tuple(g) == (1, 1, 1)
+    g, h = deflation_boxes([0, 0, 0], [6, 6, 6], [1, 1, 1], 10 ** 6)
+    assert tuple(g) == (2, 2, 2) and (h >= 2.0).all()
+    # the dense coarse problem is capped at 16384 unknowns
+    g, _ = deflation_boxes([0, 0, 0], [1, 1, 1], [1e-3] * 3, 10 ** 6)
+    assert 6 * np.prod(g) <= 16384
+    # explicit grid is clipped by the same rules
+    g, _ = deflation_boxes([0, 0, 0], [10, 10, 10], [1, 1, 1], grid=(8, 8, 8))
+    assert tuple(g) == (4, 4, 4)
