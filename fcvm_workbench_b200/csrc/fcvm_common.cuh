@@ -152,8 +152,10 @@ struct fcvm_ctx {
   int32_t *d_cid = nullptr;     // [nn] cluster of each node
   int32_t *cl_ptr = nullptr, *cl_nodes = nullptr;     // nodes of each cluster, ascending
   int8_t *kz_rel = nullptr;     // [nn][8] relative position code (0..26) of the cluster a slot couples to, -1 unused
-  double *kz_val = nullptr;     // [nn][8][18] (K Z)_(i, cluster): 3 x 6
-  int32_t *ent_ptr = nullptr, *ent = nullptr;         // per target cluster: entries i*8+t, ascending
+  double *kz_val = nullptr;     // [18][nent] (K Z)_(i, cluster) 3 x 6, entry-ordered, component-major
+  int32_t *ent_ptr = nullptr, *ent = nullptr;         // per target cluster: its entries (node of each), ascending
+  int32_t *ent_inv = nullptr;   // [nn][8] (node, slot) -> entry, -1 = dropped
+  int64_t nent = 0;
   double *dE = nullptr, *dEinv = nullptr;             // [6 ncl][6 ncl]
   double *d_rhs = nullptr, *d_lam = nullptr;          // [6 ncl]
   double *spmv_part2 = nullptr; // per-slice partials of r.u

@@ -56,11 +56,16 @@ __device__ __forceinline__ int32_t neighbour(const Grid &g, int32_t cl, int code
   return ix + nx * (iy + ny * iz);
 }
 
-// (K Z)_(i, c') for every block row i: one thread per row, walking its SELL slice
+// (K Z)_(i, c') for every block row i: one thread per row, walking its SELL slice.  Slot t of a row is
+// the t-th distinct box met along the row (purely structural).  Structure pass (ent_inv == nullptr):
+// only the relative box codes are written, slots whose 3x6 block vanishes -- a rigid motion of a box
+// leaves the nodes in its interior force-free -- get -1.  Value pass: the blocks of the kept slots go to
+// the entry-ordered, component-major array kzs[q][entry] that the per-iteration kernel streams.
 __global__ void k_build_kz(int64_t nslices, Grid g, const int32_t *__restrict__ slice_ptr, const int32_t *__restrict__ slot_node,
                            const int32_t *__restrict__ colidx, const double *__restrict__ vals,
                            const double *__restrict__ xyz, const double *__restrict__ fixdof,
-                           const int32_t *__restrict__ cid, int8_t *__restrict__ kz_rel, double *__restrict__ kz_val,
+                           const int32_t *__restrict__ cid, int8_t *__restrict__ kz_rel,
+                           const int32_t *__restrict__ ent_inv, double *__restrict__ kzs, int64_t nent,
                            int *__restrict__ err) {
   const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t s = slot / SELL_C;
@@ -72,6 +77,7 @@ __global__ void k_build_kz(int64_t nslices, Grid g, const int32_t *__restrict__ 
   int8_t codes[8];
   double acc[8][18];
   int used = 0;
+  double amax = 0.0;
   for (int t = 0; t < 8; t++) {
     codes[t] = -1;
     for (int q = 0; q < 18; q++) acc[t][q] = 0.0;
@@ -80,13 +86,11 @@ __global__ void k_build_kz(int64_t nslices, Grid g, const int32_t *__restrict__ 
     const int64_t pos = (int64_t)k * SELL_C + lane;
     const double *v = vals + (int64_t)k * 9 * SELL_C + lane;
     double a[9];
-    bool nz = false;
     for (int q = 0; q < 9; q++) {
       a[q] = v[q * SELL_C];
-      nz |= a[q] != 0.0;
+      amax = fmax(amax, fabs(a[q]));
     }
-    if (!nz) continue;                               // padding / eliminated block
-    const int32_t j = colidx[pos];
+    const int32_t j = colidx[pos];                   // padding entries point at the row's own node
     const int32_t cj = cid[j];
     const int code = rel_code(g, ci, cj);
     if (code < 0) { atomicExch(err, 1); continue; }
@@ -101,12 +105,18 @@ __global__ void k_build_kz(int64_t nslices, Grid g, const int32_t *__restrict__ 
     for (int r = 0; r < 3; r++)
       for (int m = 0; m < 6; m++) acc[t][6 * r + m] += a[3 * r] * Z[0][m] + a[3 * r + 1] * Z[1][m] + a[3 * r + 2] * Z[2][m];
   }
-  for (int t = 0; t < 8; t++) {
-    // slots whose block vanishes (a rigid motion of the cluster leaves an interior node force-free) are dropped
-    double mx = 0.0;
-    for (int q = 0; q < 18; q++) mx = fmax(mx, fabs(acc[t][q]));
-    kz_rel[8 * (int64_t)row + t] = (t < used && mx > 0.0) ? codes[t] : (int8_t)-1;
-    for (int q = 0; q < 18; q++) kz_val[(8 * (int64_t)row + t) * 18 + q] = acc[t][q];
+  if (!ent_inv) {
+    for (int t = 0; t < 8; t++) {
+      double mx = 0.0;
+      for (int q = 0; q < 18; q++) mx = fmax(mx, fabs(acc[t][q]));
+      kz_rel[8 * (int64_t)row + t] = (t < used && mx > 1e-13 * amax) ? codes[t] : (int8_t)-1;
+    }
+  } else {
+    for (int t = 0; t < 8; t++) {
+      const int32_t idx = ent_inv[8 * (int64_t)row + t];
+      if (idx < 0) continue;
+      for (int q = 0; q < 18; q++) kzs[(int64_t)q * nent + idx] = acc[t][q];
+    }
   }
 }
 
@@ -114,8 +124,8 @@ __global__ void k_build_kz(int64_t nslices, Grid g, const int32_t *__restrict__ 
 // list order, thread (t, entry) adds slot t's 6x6 contribution to the accumulator of its neighbour code
 __global__ void __launch_bounds__(288)
 k_build_e(Grid g, int64_t ncl, const int32_t *__restrict__ cl_ptr, const int32_t *__restrict__ cl_nodes,
-          const int8_t *__restrict__ kz_rel, const double *__restrict__ kz_val, const double *__restrict__ xyz,
-          const double *__restrict__ fixdof, double *__restrict__ E) {
+          const int8_t *__restrict__ kz_rel, const int32_t *__restrict__ ent_inv, const double *__restrict__ kzs,
+          int64_t nent, const double *__restrict__ xyz, const double *__restrict__ fixdof, double *__restrict__ E) {
   __shared__ double acc[27][36];
   const int c = blockIdx.x;
   for (int q = threadIdx.x; q < 27 * 36; q += blockDim.x) (&acc[0][0])[q] = 0.0;
@@ -127,8 +137,8 @@ k_build_e(Grid g, int64_t ncl, const int32_t *__restrict__ cl_ptr, const int32_t
     if (code >= 0) {
       double Z[3][6];
       z_of(g, c, xyz, fixdof, i, Z);
-      const double *kz = kz_val + (8 * i + t) * 18;
-      acc[code][e] += Z[0][a] * kz[b] + Z[1][a] * kz[6 + b] + Z[2][a] * kz[12 + b];
+      const double *kz = kzs + ent_inv[8 * i + t];
+      acc[code][e] += Z[0][a] * kz[b * nent] + Z[1][a] * kz[(6 + b) * nent] + Z[2][a] * kz[(12 + b) * nent];
     }
     __syncthreads();
   }
@@ -161,7 +171,8 @@ __global__ void k_mirror(int64_t n, const double *__restrict__ L, double *__rest
 // rhs_c = sum_{i in c} w_i Z_i^T r_i  -  sum_{(i,t) -> c} (K Z)_(i,t)^T y_i        (one block per cluster)
 __global__ void __launch_bounds__(256)
 k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restrict__ cl_nodes,
-             const int32_t *__restrict__ ent_ptr, const int32_t *__restrict__ ent, const double *__restrict__ kz_val,
+             const int32_t *__restrict__ ent_ptr, const int32_t *__restrict__ ent_node, const double *__restrict__ kzs,
+             int64_t nent,
              const double *__restrict__ xyz, const double *__restrict__ fixdof, const double *__restrict__ wt,
              const double *__restrict__ r, const double *__restrict__ y, double *__restrict__ rhs,
              const double *__restrict__ sc, int done_slot) {
@@ -178,13 +189,14 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
     for (int m = 0; m < 6; m++) v[m] += Z[0][m] * r0 + Z[1][m] * r1 + Z[2][m] * r2;
   }
   if (y) {
+    // entries of this box: consecutive lanes read consecutive doubles of each of the 18 component planes
     for (int32_t idx = ent_ptr[c] + threadIdx.x; idx < ent_ptr[c + 1]; idx += 256) {
-      const int64_t it = ent[idx];
-      const int64_t i = it >> 3;
-      const double *kz = kz_val + it * 18;
+      const int64_t i = ent_node[idx];
+      const double *kz = kzs + idx;
       const double y0 = y[3 * i], y1 = y[3 * i + 1], y2 = y[3 * i + 2];
 #pragma unroll
-      for (int m = 0; m < 6; m++) v[m] -= kz[m] * y0 + kz[6 + m] * y1 + kz[12 + m] * y2;
+      for (int m = 0; m < 6; m++)
+        v[m] -= __ldcs(kz + m * nent) * y0 + __ldcs(kz + (6 + m) * nent) * y1 + __ldcs(kz + (12 + m) * nent) * y2;
     }
   }
   __shared__ double sm[6][8];
@@ -290,7 +302,7 @@ extern "C" int fcvm_set_deflation(fcvm_ctx *c, int ncx, int ncy, int ncz, const 
   FCVM_CUDA(cudaMemcpy(c->d_cid, cid, sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
   FCVM_CUDA(cudaMemcpy(c->cl_ptr, ptr.data(), sizeof(int32_t) * (ncl + 1), cudaMemcpyHostToDevice));
   FCVM_CUDA(cudaMemcpy(c->cl_nodes, nodes.data(), sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
-  FCVM_TRY(dalloc2(&c->kz_rel, 8 * nn)); FCVM_TRY(dalloc2(&c->kz_val, 8 * 18 * nn));
+  FCVM_TRY(dalloc2(&c->kz_rel, 8 * nn));
   FCVM_TRY(dalloc2(&c->dE, 36 * ncl * ncl)); FCVM_TRY(dalloc2(&c->dEinv, 36 * ncl * ncl));
   FCVM_TRY(dalloc2(&c->d_rhs, 6 * ncl)); FCVM_TRY(dalloc2(&c->d_lam, 6 * ncl));
   FCVM_TRY(dalloc2(&c->spmv_part2, c->nslices + 8));
@@ -311,18 +323,22 @@ int deflation_build(fcvm_ctx *c) {
   int *derr;
   FCVM_CUDA(cudaMalloc((void **)&derr, sizeof(int)));
   FCVM_CUDA(cudaMemsetAsync(derr, 0, sizeof(int), st));
-  k_build_kz<<<grid_for(c->nslices * SELL_C, 128), 128, 0, st>>>(c->nslices, g, c->slice_ptr, c->slot_node, c->colidx,
-                                                                c->vals, c->xyz, fixdof, c->d_cid, c->kz_rel, c->kz_val,
-                                                                derr);
-  int herr = 0;
-  FCVM_CUDA(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
-  FCVM_CUDA(cudaStreamSynchronize(st));
-  cudaFree(derr);
-  FCVM_CHECK(herr == 0, FCVM_E_ARG,
-             "deflation: a node couples to %s -- the clusters must be at least two elements wide in every direction",
-             herr == 1 ? "a cluster that is not a neighbour of its own" : "more than eight clusters");
+  auto check = [&]() -> int {
+    int herr = 0;
+    FCVM_CUDA(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FCVM_CUDA(cudaStreamSynchronize(st));
+    FCVM_CHECK(herr == 0, FCVM_E_ARG,
+               "deflation: a node couples to %s -- the clusters must be at least two elements wide in every direction",
+               herr == 1 ? "a cluster that is not a neighbour of its own" : "more than eight clusters");
+    return FCVM_OK;
+  };
   if (!c->defl_structure) {
-    // per target cluster: the (node, slot) entries that point to it, ascending (fixed reduction order)
+    // structure pass: which (node, slot) pairs carry a non-vanishing block, and per target box the list
+    // of those entries in ascending (node, slot) order -- the fixed order of every later reduction
+    k_build_kz<<<grid_for(c->nslices * SELL_C, 128), 128, 0, st>>>(c->nslices, g, c->slice_ptr, c->slot_node, c->colidx,
+                                                                  c->vals, c->xyz, fixdof, c->d_cid, c->kz_rel, nullptr,
+                                                                  nullptr, 0, derr);
+    if (int rc = check()) { cudaFree(derr); return rc; }
     std::vector<int8_t> rel((size_t)8 * nn);
     std::vector<int32_t> cid((size_t)nn);
     FCVM_CUDA(cudaMemcpy(rel.data(), c->kz_rel, (size_t)8 * nn, cudaMemcpyDeviceToHost));
@@ -335,16 +351,30 @@ int deflation_build(fcvm_ctx *c) {
     for (int64_t it = 0; it < 8 * nn; it++)
       if (rel[(size_t)it] >= 0) ptr[(size_t)target(cid[(size_t)(it >> 3)], rel[(size_t)it]) + 1]++;
     for (int64_t k = 0; k < ncl; k++) ptr[(size_t)k + 1] += ptr[(size_t)k];
-    std::vector<int32_t> ent((size_t)std::max<int32_t>(ptr[(size_t)ncl], 1)), fill(ptr.begin(), ptr.end() - 1);
+    const int64_t nent = std::max<int64_t>(ptr[(size_t)ncl], 1);
+    std::vector<int32_t> ent_node((size_t)nent, 0), inv((size_t)8 * nn, -1), fill(ptr.begin(), ptr.end() - 1);
     for (int64_t it = 0; it < 8 * nn; it++)
-      if (rel[(size_t)it] >= 0) ent[(size_t)fill[(size_t)target(cid[(size_t)(it >> 3)], rel[(size_t)it])]++] = (int32_t)it;
-    FCVM_TRY(dalloc2(&c->ent_ptr, ncl + 1)); FCVM_TRY(dalloc2(&c->ent, (int64_t)ent.size()));
+      if (rel[(size_t)it] >= 0) {
+        const int32_t idx = fill[(size_t)target(cid[(size_t)(it >> 3)], rel[(size_t)it])]++;
+        ent_node[(size_t)idx] = (int32_t)(it >> 3);
+        inv[(size_t)it] = idx;
+      }
+    c->nent = nent;
+    FCVM_TRY(dalloc2(&c->ent_ptr, ncl + 1)); FCVM_TRY(dalloc2(&c->ent, nent)); FCVM_TRY(dalloc2(&c->ent_inv, 8 * nn));
+    FCVM_TRY(dalloc2(&c->kz_val, 18 * nent));
     FCVM_CUDA(cudaMemcpy(c->ent_ptr, ptr.data(), sizeof(int32_t) * (ncl + 1), cudaMemcpyHostToDevice));
-    FCVM_CUDA(cudaMemcpy(c->ent, ent.data(), sizeof(int32_t) * ent.size(), cudaMemcpyHostToDevice));
+    FCVM_CUDA(cudaMemcpy(c->ent, ent_node.data(), sizeof(int32_t) * nent, cudaMemcpyHostToDevice));
+    FCVM_CUDA(cudaMemcpy(c->ent_inv, inv.data(), sizeof(int32_t) * 8 * nn, cudaMemcpyHostToDevice));
     c->defl_structure = true;
   }
+  k_build_kz<<<grid_for(c->nslices * SELL_C, 128), 128, 0, st>>>(c->nslices, g, c->slice_ptr, c->slot_node, c->colidx,
+                                                                c->vals, c->xyz, fixdof, c->d_cid, c->kz_rel, c->ent_inv,
+                                                                c->kz_val, c->nent, derr);
+  if (int rc = check()) { cudaFree(derr); return rc; }
+  cudaFree(derr);
   FCVM_CUDA(cudaMemsetAsync(c->dE, 0, sizeof(double) * n6 * n6, st));
-  k_build_e<<<(unsigned)ncl, 288, 0, st>>>(g, ncl, c->cl_ptr, c->cl_nodes, c->kz_rel, c->kz_val, c->xyz, fixdof, c->dE);
+  k_build_e<<<(unsigned)ncl, 288, 0, st>>>(g, ncl, c->cl_ptr, c->cl_nodes, c->kz_rel, c->ent_inv, c->kz_val, c->nent, c->xyz,
+                                           fixdof, c->dE);
   if (c->world > 1) FCVM_TRY(fcvm_comm_allreduce_sum(c, c->dE, n6 * n6));
   k_sym_guard<<<grid_for(n6 * n6, 256), 256, 0, st>>>(n6, c->dE);
   FCVM_CUDA(cudaGetLastError());
@@ -387,7 +417,7 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
   const Grid g = grid_of(c);
   const double *fixdof = (const double *)c->buf[FCVM_BUF_FIXDOF];
   const int64_t n6 = 6 * c->ncl;
-  k_coarse_rhs<<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val, c->xyz, fixdof,
+  k_coarse_rhs<<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val, c->nent, c->xyz, fixdof,
                                                 c->dof_weight, r, y, c->d_rhs, sc, done_slot);
   if (c->world > 1) FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_rhs, n6));
   k_gemv<<<grid_for(n6, 8), 256, 0, st>>>(n6, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
@@ -399,7 +429,7 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
 
 void deflation_free(fcvm_ctx *c) {
   cudaFree(c->d_cid); cudaFree(c->cl_ptr); cudaFree(c->cl_nodes); cudaFree(c->kz_rel); cudaFree(c->kz_val);
-  cudaFree(c->ent_ptr); cudaFree(c->ent); cudaFree(c->dE); cudaFree(c->dEinv); cudaFree(c->d_rhs); cudaFree(c->d_lam);
+  cudaFree(c->ent_ptr); cudaFree(c->ent); cudaFree(c->ent_inv); c->ent_inv = nullptr; cudaFree(c->dE); cudaFree(c->dEinv); cudaFree(c->d_rhs); cudaFree(c->d_lam);
   cudaFree(c->spmv_part2);
   c->d_cid = c->cl_ptr = c->cl_nodes = c->ent_ptr = c->ent = nullptr;
   c->kz_rel = nullptr;
