@@ -326,6 +326,39 @@ __device__ __forceinline__ void store_gradient_tile(const GPCoef &c, const doubl
   }
 }
 
+// the same for two Gauss points at once: every staged value is read once and feeds both
+__device__ __forceinline__ void local_gradient_tile2(const GPCoef &a, const GPCoef &b, const double *tile, int stride,
+                                                     double (&oa)[3][3], double (&ob)[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double v0 = tile[(0 + i) * stride], v1 = tile[(3 + i) * stride], v2 = tile[(6 + i) * stride];
+    const double v3 = tile[(9 + i) * stride], v4 = tile[(12 + i) * stride], v5 = tile[(15 + i) * stride];
+    const double v6 = tile[(18 + i) * stride], v7 = tile[(21 + i) * stride], v8 = tile[(24 + i) * stride];
+    const double v9 = tile[(27 + i) * stride];
+    const double d56 = v5 - v6, d87 = v8 - v7, d54 = v5 - v4, d97 = v9 - v7;
+    oa[i][0] = a.a4 * v0 + a.d01 * v1 + a.d04 * v4 + a.e4 * d56 + a.z4 * d87;
+    oa[i][1] = a.a4 * v0 + a.d12 * v2 + a.x4 * d54 + a.d16 * v6 + a.z4 * d97;
+    oa[i][2] = a.a4 * v0 + a.d23 * v3 - a.x4 * v4 - a.e4 * v6 + a.d27 * v7 + a.x4 * v8 + a.e4 * v9;
+    ob[i][0] = b.a4 * v0 + b.d01 * v1 + b.d04 * v4 + b.e4 * d56 + b.z4 * d87;
+    ob[i][1] = b.a4 * v0 + b.d12 * v2 + b.x4 * d54 + b.d16 * v6 + b.z4 * d97;
+    ob[i][2] = b.a4 * v0 + b.d23 * v3 - b.x4 * v4 - b.e4 * v6 + b.d27 * v7 + b.x4 * v8 + b.e4 * v9;
+  }
+}
+
+// F[3k+i] (+)= sum_j T[i][j] * dN[j][k] in registers
+template <bool ACC>
+__device__ __forceinline__ void gradient_to_regs(const GPCoef &c, const double (&T)[3][3], double (&F)[30]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double t0 = T[i][0], t1 = T[i][1], t2 = T[i][2];
+    const double f[10] = {c.a4 * (t0 + t1 + t2), c.d01 * t0, c.d12 * t1, c.d23 * t2, c.d04 * t0 - c.x4 * (t1 + t2),
+                          c.e4 * t0 + c.x4 * t1, c.d16 * t1 - c.e4 * (t0 + t2), c.d27 * t2 - c.z4 * (t0 + t1),
+                          c.z4 * t0 + c.x4 * t2, c.z4 * t1 + c.e4 * t2};
+#pragma unroll
+    for (int k = 0; k < 10; k++) F[3 * k + i] = ACC ? F[3 * k + i] + f[k] : f[k];
+  }
+}
+
 // determinant and inverse of the Jacobian xs[i][j] = d x_i / d xi_j   (fcVM.py:428-453)
 __device__ __forceinline__ double invert_jacobian(const double (&xs)[3][3], double (&xsi)[3][3]) {
   double xsj = (xs[0][0] * xs[1][1] * xs[2][2] - xs[0][0] * xs[1][2] * xs[2][1] + xs[0][2] * xs[1][0] * xs[2][1] -

@@ -39,11 +39,11 @@ constexpr int SU_PAD = 33;          // row stride of the force staging (conflict
 // One Gauss point of one element (lane = element, GP = warp): (convected) old stress, elastic test
 // stress, radial return; leaves this point's share of the element force vector in shared memory.
 template <bool LD>
-__device__ __forceinline__ void gauss_point(int64_t ne, int64_t e, int GP, bool live, const GPCoef &cf,
-                                            const double (&xsi)[3][3], double xsj, const double (&g)[3][3],
-                                            double (&sc)[6], double sy, const Material &m,
-                                            double *__restrict__ sig_new, double *__restrict__ sig_test,
-                                            uint8_t *__restrict__ pgp, double *sF) {
+__device__ __forceinline__ void gauss_point_T(int64_t ne, int64_t e, int GP, bool live, const double (&xsi)[3][3],
+                                              double xsj, const double (&g)[3][3], double (&sc)[6], double sy,
+                                              const Material &m, double *__restrict__ sig_new,
+                                              double *__restrict__ sig_test, uint8_t *__restrict__ pgp,
+                                              double (&T)[3][3]) {
   const double deps0 = g[0][0], deps1 = g[1][1], deps2 = g[2][2];
   const double deps3 = g[0][1] + g[1][0], deps4 = g[0][2] + g[2][0], deps5 = g[1][2] + g[2][1];
   if (LD) {
@@ -105,11 +105,20 @@ __device__ __forceinline__ void gauss_point(int64_t ne, int64_t e, int GP, bool 
   // element force of this Gauss point: F[k][i] = w|J| sum_mm S[i][mm] dshpg[mm][k]   (fcVM.py:2448-2454)
   const double w = GP_W * fabs(xsj);
   const double S[3][3] = {{sxx, sxy, szx}, {sxy, syy, syz}, {szx, syz, szz}};
-  double T[3][3];
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) T[i][j] = w * (S[i][0] * xsi[j][0] + S[i][1] * xsi[j][1] + S[i][2] * xsi[j][2]);
+}
+
+template <bool LD>
+__device__ __forceinline__ void gauss_point(int64_t ne, int64_t e, int GP, bool live, const GPCoef &cf,
+                                            const double (&xsi)[3][3], double xsj, const double (&g)[3][3],
+                                            double (&sc)[6], double sy, const Material &m,
+                                            double *__restrict__ sig_new, double *__restrict__ sig_test,
+                                            uint8_t *__restrict__ pgp, double *sF) {
+  double T[3][3];
+  gauss_point_T<LD>(ne, e, GP, live, xsi, xsj, g, sc, sy, m, sig_new, sig_test, pgp, T);
   store_gradient_tile(cf, T, sF, SU_PAD);
 }
 
@@ -196,6 +205,98 @@ k_stress_update(int64_t ne, const int32_t *__restrict__ conn, const double *__re
   }
 }
 
+// Variant with two Gauss points per thread: block = 32 elements x 2 warps, warp p integrates points 2p and
+// 2p+1.  The staged nodal values are read once for both points, the two force contributions are added in
+// registers, so half as much data crosses the shared-memory pipe (the unit that bounds the four-warp
+// kernel); the price is twice the work and ~2x the registers per thread.
+constexpr int SP_THREADS = 64;
+template <bool LD>
+__global__ void __launch_bounds__(SP_THREADS, 6)
+k_stress_update_pair(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
+                     const double *__restrict__ disp, const double *__restrict__ du, Material m,
+                     const double *__restrict__ sig_old, const double *__restrict__ sig_yield, double yield_scale,
+                     double *__restrict__ sig_new, double *__restrict__ sig_test, uint8_t *__restrict__ pgp,
+                     double *__restrict__ elv) {
+  __shared__ double smem[2 * SU_E * SU_ROW];      // nodal staging [2][32][35], then force staging [2][30][33]
+  double *sX = smem, *sU = smem + SU_E * SU_ROW;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t e0 = (int64_t)blockIdx.x * SU_E;
+  const bool live = e0 + lane < ne;
+  const int64_t e = min(e0 + lane, ne - 1);
+  const int gpa = 2 * warp, gpb = gpa + 1;
+  // state of the first point is requested before the gather
+  double sc[6];
+#pragma unroll
+  for (int c = 0; c < 6; c++) sc[c] = __ldcs(&sig_old[((int64_t)c * 4 + gpa) * ne + e]);
+  double sy = yield_scale * __ldcs(&sig_yield[(int64_t)gpa * ne + e]);
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    constexpr int NQ = 8;                          // 960 items / 64 threads = 15 = 8 + 7
+    int64_t d[NQ];
+#pragma unroll
+    for (int r = 0; r < NQ; r++) {
+      const int q = min(tid + (half * NQ + r) * SP_THREADS, 30 * SU_E - 1);
+      const int p = q / 3;
+      d[r] = 3 * (int64_t)conn[(int64_t)(p >> 5) * ne + min(e0 + (p & 31), ne - 1)] + (q - 3 * p);
+    }
+    double xv[NQ], uv[NQ];
+#pragma unroll
+    for (int r = 0; r < NQ; r++) {
+      xv[r] = xyz[d[r]];
+      if (LD) xv[r] += disp[d[r]];
+      uv[r] = du[d[r]];
+    }
+#pragma unroll
+    for (int r = 0; r < NQ; r++) {
+      const int q = tid + (half * NQ + r) * SP_THREADS;
+      if (q < 30 * SU_E) {
+        const int p = q / 3;
+        const int at = (p & 31) * SU_ROW + 3 * (p >> 5) + (q - 3 * p);
+        sX[at] = xv[r];
+        sU[at] = uv[r];
+      }
+    }
+  }
+  __syncthreads();
+  const GPCoef ca = gp_coef(gpa), cb = gp_coef(gpb);
+  double xsiA[3][3], xsiB[3][3], gA[3][3], gB[3][3], xsjA, xsjB;
+  {
+    double xa[3][3], xb[3][3];
+    local_gradient_tile2(ca, cb, sX + lane * SU_ROW, 1, xa, xb);
+    xsjA = invert_jacobian(xa, xsiA);
+    xsjB = invert_jacobian(xb, xsiB);
+    local_gradient_tile2(ca, cb, sU + lane * SU_ROW, 1, xa, xb);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int mm = 0; mm < 3; mm++) {
+        gA[i][mm] = xa[i][0] * xsiA[0][mm] + xa[i][1] * xsiA[1][mm] + xa[i][2] * xsiA[2][mm];
+        gB[i][mm] = xb[i][0] * xsiB[0][mm] + xb[i][1] * xsiB[1][mm] + xb[i][2] * xsiB[2][mm];
+      }
+  }
+  __syncthreads();      // staged nodal data consumed: the force staging may overwrite it
+  double F[30], T[3][3];
+  gauss_point_T<LD>(ne, e, gpa, live, xsiA, xsjA, gA, sc, sy, m, sig_new, sig_test, pgp, T);
+  gradient_to_regs<false>(ca, T, F);
+  // (requesting the second point's state ahead of the first point's arithmetic measured slower: registers)
+#pragma unroll
+  for (int c = 0; c < 6; c++) sc[c] = __ldcs(&sig_old[((int64_t)c * 4 + gpb) * ne + e]);
+  sy = yield_scale * __ldcs(&sig_yield[(int64_t)gpb * ne + e]);
+  gauss_point_T<LD>(ne, e, gpb, live, xsiB, xsjB, gB, sc, sy, m, sig_new, sig_test, pgp, T);
+  gradient_to_regs<true>(cb, T, F);
+  double *sF = smem + (warp * 30) * SU_PAD + lane;
+#pragma unroll
+  for (int k = 0; k < 30; k++) sF[k * SU_PAD] = F[k];
+  __syncthreads();
+  const int nlive = (int)min((int64_t)SU_E, ne - e0) * 30;
+  double *out = elv + 30 * e0;
+  for (int idx = tid; idx < nlive; idx += SP_THREADS) {
+    const int el = idx / 30, k3 = idx - 30 * el;
+    const double *f = smem + k3 * SU_PAD + el;
+    out[idx] = f[0] + f[30 * SU_PAD];
+  }
+}
+
 }  // namespace
 
 // Deterministic assembly of nodal vectors: dof d = 3*node+c sums the element vectors of the
@@ -235,7 +336,17 @@ extern "C" int fcvm_update_stress_load(fcvm_ctx *c, const double *disp_new, cons
   {
     ProfScope ps(c, 1);
     const int grid = grid_for(c->ne, SU_E);
-    if (LD)
+    // default: two Gauss points per thread (0.265 ms at 1M elements); FCVM_STRESS_PAIR=0 selects the
+    // four-warp kernel (0.277 ms) for comparison
+    static const bool pair = !(getenv("FCVM_STRESS_PAIR") && atoi(getenv("FCVM_STRESS_PAIR")) == 0);
+    if (pair) {
+      if (LD)
+        k_stress_update_pair<true><<<grid, SP_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
+                                                                     yield_scale, sn, stt, pg, c->elv);
+      else
+        k_stress_update_pair<false><<<grid, SP_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
+                                                                      yield_scale, sn, stt, pg, c->elv);
+    } else if (LD)
       k_stress_update<true><<<grid, SU_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
                                                                 yield_scale, sn, stt, pg, c->elv);
     else
