@@ -58,7 +58,8 @@ def main(argv=None):
     say(f"{name}: {m.ne} elements, {m.nn} nodes ({time.time() - t0:.2f} s input)")
     t0 = time.time()
     with fcVM.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix, device=a.device) as eng:
-        res = fcVM.calcDisp(m, ctl, clicks=clicks, engine=eng, rtol=a.rtol, log=say)
+        res = fcVM.calcDisp(m, ctl, clicks=clicks, engine=eng, rtol=a.rtol, log=say,
+                            deflation=fcVM.AUTO_DEFLATION if m.nn >= 20000 else 0)
         t1 = time.time()
         averaged = ctl.averaged_option == "averaged"
         for which, key in ((fcVM.SIG_NEW, "stresses"), (fcVM.PEEQ, "peeq"), (fcVM.SIGMISES, "sigmises"), (fcVM.CSR, "csr")):

@@ -35,6 +35,9 @@ from .loads import surface_load_vector
 SIG_OLD, SIG_NEW, SIG_TEST, SIG_YIELD, PEEQ, CSR, TRIAX, PRESSURE, SIGMISES, ECR, PGP, MODF, GLV, FIXDOF = range(14)
 
 
+AUTO_DEFLATION = 6144      # coarse unknowns calcDisp asks for by default on large meshes
+
+
 class StopAnalysis(Exception):
     """Raised from an ``on_iteration`` hook to end the analysis early (a scripted "stop" click)."""
 
@@ -518,7 +521,7 @@ def mapStresses(averaged, elNodes, nocoord, sig, peeq, sigvm, csr, noce, sig_yie
 # calcDisp: the load-stepping driver (fcVM.py:1083-1635), vectors resident on the device.
 # ----------------------------------------------------------------------------------------------
 def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=None, engine: Optional[Engine] = None,
-             comm=None, on_iteration=None, deflation: Optional[int] = None):
+             comm=None, on_iteration=None, deflation="auto"):
     """Run the whole load-displacement analysis on the GPU.
 
     Same control flow as the reference (arc-length corrected modified Newton with restarts,
@@ -532,6 +535,10 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
     eng = engine or Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix, device=device, comm=comm)
     if not own:
         eng.set_constraints(m.fix)
+    if deflation == "auto":
+        # second preconditioner level (rigid-body-mode deflation) once the mesh is large enough
+        # for boxes two elements wide to be worth it; an engine handed in keeps whatever its owner chose
+        deflation = (AUTO_DEFLATION if eng.nn * (comm.world if comm is not None else 1) >= 20000 else 0) if own else None
     if deflation is not None and hasattr(eng, "set_deflation"):
         eng.set_deflation(deflation)
     ndof, nelem = eng.ndof, eng.ne
