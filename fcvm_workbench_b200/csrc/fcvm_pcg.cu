@@ -107,11 +107,20 @@ __global__ void __launch_bounds__(1024)
 k_dot_finish(int64_t n, const double *__restrict__ part, const double *__restrict__ part2, double *sc, int delta_slot,
              int gamma_slot, double *tail) {
   if (sc[S_ITERS] >= 0.0) return;
-  double t = 0.0, g = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += 1024) {
-    t += part[i];
-    if (part2) g += part2[i];
+  // four independent partial sums per thread (fixed interleave) keep the loads in flight; the order of the
+  // additions is fixed by n alone
+  double ta[4] = {0, 0, 0, 0}, ga[4] = {0, 0, 0, 0};
+  for (int64_t i0 = threadIdx.x; i0 < n; i0 += 4 * 1024) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int64_t i = i0 + u * 1024;
+      if (i < n) {
+        ta[u] += part[i];
+        if (part2) ga[u] += part2[i];
+      }
+    }
   }
+  double t = (ta[0] + ta[1]) + (ta[2] + ta[3]), g = (ga[0] + ga[1]) + (ga[2] + ga[3]);
   __shared__ double sm[2][32];
   t = warp_sum(t);
   g = warp_sum(g);
