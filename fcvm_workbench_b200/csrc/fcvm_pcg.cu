@@ -1,10 +1,13 @@
 // Block-SELL SpMV and the on-device preconditioned conjugate-gradient solve that replaces
 // factor = cholesky(gsm); x = factor(b)   (fcVM.py:1121-1135, 1264-1278, 1369-1406).
 //
-// The loop runs without host round trips: step lengths live in device scalars, every dot
-// product is a fixed-shape two-stage reduction (bit-reproducible), and a device flag turns
-// the remaining launches of a batch into no-ops once the tolerance is met.  The host only
-// polls that flag every CHECK_EVERY iterations.
+// Single-reduction (Chronopoulos-Gear) preconditioned CG: per iteration one SpMV w = K u -- which also
+// leaves the partial sums of w.u (and r.u) -- and one vector kernel (k_pcg_step).  The loop runs without
+// host round trips: step lengths live in device scalars, every dot product is a fixed-shape reduction
+// (bit-reproducible), and a device flag turns the remaining launches of a batch into no-ops once the
+// tolerance is met; the host only polls every CHECK_EVERY iterations.  Preconditioner: block-Jacobi, plus
+// the rigid-body-mode deflation level of fcvm_deflation.cu when switched on.  On a partitioned mesh the
+// interface exchange of w overlaps the interior part of the product (communication stream).
 #include "fcvm_common.cuh"
 #include "fcvm_reduce.cuh"
 
@@ -20,7 +23,7 @@ namespace {
 constexpr int CHECK_EVERY = 16;
 
 // Device scalar slots in ctx->red_out.  gamma = r.u, rr = r.r and alpha live in pairs indexed by
-// the parity of the iteration; L_* are per-rank partial sums that travel with the interface
+// the parity of the iteration; L_* are per-rank partial sums on their way through the three-scalar
 // all-reduce when a communicator is attached.
 enum {
   S_GAMMA = 0,   // [2]

@@ -136,8 +136,9 @@ int fcvm_export_csc_lower(fcvm_ctx *ctx, int64_t *nnz, int64_t *indptr, int64_t 
 int fcvm_spmv(fcvm_ctx *ctx, const double *x, double *y);
 
 /* ---- linear solve: replaces factor = cholesky(gsm); x = factor(b) (fcVM.py:1121-1135, 1401) -- */
-/* Block-Jacobi preconditioned CG on the device.  x is overwritten (initial guess zero unless
- * use_x0).  Converged when ||b - K x|| <= rtol * ||b||. */
+/* Preconditioned CG on the device (single-reduction form; block-Jacobi, plus the deflation level below
+ * when switched on).  x is overwritten (initial guess zero unless use_x0).  Converged when the
+ * recursively updated residual satisfies ||r|| <= rtol * ||b||; returns FCVM_E_NOCONV after max_iter. */
 int fcvm_pcg_solve(fcvm_ctx *ctx, const double *b, double *x, double rtol, int max_iter, int use_x0, int *iters,
                    double *relres);
 
