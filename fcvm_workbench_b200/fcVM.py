@@ -553,8 +553,6 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
             raise NotImplementedError("eigen-buckling pre-analysis (GNLY with imperfection) is outside this path")
     else:
         LD = False
-    if float(nstep) == 1.0:
-        raise NotImplementedError("single-step elastic analysis is outside this path")
 
     def load_vector(disp_host=None):
         return surface_load_vector(m.nocoord, m.loadfaces, m.pressure, m.loadvertices, m.vertexloads, m.loadedges,
@@ -599,15 +597,22 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
     lbd = [0.0]
     rfl = [0.0]
     iters, nplastic, pcg_its = [], [], []
-    # the reference's elastic "warm-up" call (fcVM.py:1195-1197) only produces values that are
-    # overwritten before use (sig_new, pgp are reset at fcVM.py:1301-1302); it is skipped here.
     for b in (SIG_NEW, SIG_OLD, SIG_TEST):
         eng.gp_fill(b, 0.0)
+    if float(nstep) == 1.0:
+        # elastic analysis (fcVM.py:1216-1223): displacements of the elastic solve, no load stepping.  The
+        # reference wipes sig_new after its elastic stress call (fcVM.py:1195-1197, then 1300), so the
+        # returned stresses are zero there and here.
+        eng.copy(ue, disp_new)
+        lbd.append(1.0)
+        rfl.append(1.0)
+        un.append(float(np.max(np.abs(disp_el))))
+        cnt = False
     iterat_tot = 0
     mrr = False
     queue = list(clicks)
     aa = 0.0
-    lout = lbd
+    lout = [0.0] if float(nstep) == 1.0 else lbd              # fcVM.py:1193: never reassigned without load steps
 
     def record():
         res = eng.update_peeq_csr(ultimate_strain, Et_E)

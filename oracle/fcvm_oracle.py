@@ -261,8 +261,6 @@ def calcDisp(model, ctl, clicks=(), factorize: Optional[Callable] = None, log: O
             raise NotImplementedError("eigen-buckling pre-analysis (GNLY with imperfection) is outside the hot path")
     else:
         LD = False
-    if float(nstep) == 1.0:
-        raise NotImplementedError("single-step elastic analysis is outside the restated path")
 
     ndof = len(glv)
     nelem = len(elNodes)
@@ -313,8 +311,14 @@ def calcDisp(model, ctl, clicks=(), factorize: Optional[Callable] = None, log: O
 
     iterat_tot = 0
     mrr = False
-    sig_new = z24()
-    pgp = np.full(4 * nelem, False, dtype=bool)
+    if float(nstep) == 1.0:                                  # elastic analysis, fcVM.py:1216-1223
+        disp_new = ue
+        lbd = np.append(lbd, 1.0)
+        rfl = np.append(rfl, 1.0)
+        un.append(float(np.max(np.abs(disp_new))))
+        cnt = False
+    sig_new = z24()                                          # fcVM.py:1300-1301: also wipes the elastic stresses of
+    pgp = np.full(4 * nelem, False, dtype=bool)              # the call above, so nstep = 1 returns zero stresses
     queue = list(clicks)
     aa = 0.0
 

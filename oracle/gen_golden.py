@@ -17,6 +17,7 @@ Fixtures
 ``cube2_platen``   48-element block, displacement control, hardening, one restart.
 ``cube2_force``    48-element block, traction + gravity, hardening, "add" click.
 ``cube2_gnly``     large-displacement branch (calcTSM every iteration).
+``cube2_elastic``  nstep = 1: the linear-elastic analysis (no load stepping).
 ``kernels``        single calls of calcGSM (element matrices), update_stress_load
                    (LD off/on), update_PEEQ_CSR and mapStresses on a distorted mesh
                    with random state.
@@ -163,7 +164,14 @@ def main():
                   clicks=["add"])
     analysis_case("cube2_gnly", cube_model(2, mode="platen", top_disp=0.4),
                   Control(sig_yield=240.0, nstep=6, error_max=1e-6, target_LF=2.0, Et_E=0.02, gnl="GNLY"))
+    elastic_case()
     kernel_case()
+
+
+def elastic_case():
+    """nstep = 1: the reference's linear-elastic analysis (fcVM.py:1216-1223)."""
+    analysis_case("cube2_elastic", cube_model(2, mode="force", top_disp=300.0),
+                  Control(sig_yield=240.0, nstep=1, error_max=1e-6, target_LF=1.0, Et_E=0.0, grav_z=-10.0))
 
 
 if __name__ == "__main__":

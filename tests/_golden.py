@@ -7,7 +7,7 @@ from fcvm_workbench_b200.control import Control
 from fcvm_workbench_b200.model import Model
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ANALYSES = ("tensile", "cube2_platen", "cube2_force", "cube2_gnly")
+ANALYSES = ("tensile", "cube2_platen", "cube2_force", "cube2_gnly", "cube2_elastic")
 
 
 def load(name):
