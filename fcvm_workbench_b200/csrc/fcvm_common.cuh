@@ -150,6 +150,7 @@ struct fcvm_ctx {
   double dlo[3] = {0, 0, 0}, dh[3] = {1, 1, 1}, dscale = 1.0;
   int64_t ncl = 0;              // dn[0]*dn[1]*dn[2]
   int32_t *d_cid = nullptr;     // [nn] cluster of each node
+  uint8_t *cl_active = nullptr; // [ncl] box carries its six modes
   int32_t *cl_ptr = nullptr, *cl_nodes = nullptr;     // nodes of each cluster, ascending
   int8_t *kz_rel = nullptr;     // [nn][8] relative position code (0..26) of the cluster a slot couples to, -1 unused
   double *kz_val = nullptr;     // [18][nent] (K Z)_(i, cluster) 3 x 6, entry-ordered, component-major

@@ -26,6 +26,7 @@ namespace {
 struct Grid {
   int n[3];
   double lo[3], h[3], scale;
+  const uint8_t *active;     // per box: 0 = too few free nodes for six independent modes, its columns of Z are zero
 };
 
 // Z_j: 3 x 6 = [ I | (e_k x rel)/scale ], rows of prescribed dofs zeroed
@@ -35,7 +36,8 @@ __device__ __forceinline__ void z_of(const Grid &g, int32_t cl, const double *__
   const double rx = (xyz[3 * j] - (g.lo[0] + (ix + 0.5) * g.h[0])) / g.scale;
   const double ry = (xyz[3 * j + 1] - (g.lo[1] + (iy + 0.5) * g.h[1])) / g.scale;
   const double rz = (xyz[3 * j + 2] - (g.lo[2] + (iz + 0.5) * g.h[2])) / g.scale;
-  const double f0 = fixdof[3 * j], f1 = fixdof[3 * j + 1], f2 = fixdof[3 * j + 2];
+  const double on = g.active[cl] ? 1.0 : 0.0;
+  const double f0 = on * fixdof[3 * j], f1 = on * fixdof[3 * j + 1], f2 = on * fixdof[3 * j + 2];
   // e_x x r = (0, -rz, ry), e_y x r = (rz, 0, -rx), e_z x r = (-ry, rx, 0)
   Z[0][0] = f0; Z[0][1] = 0;  Z[0][2] = 0;  Z[0][3] = 0;        Z[0][4] = f0 * rz;  Z[0][5] = -f0 * ry;
   Z[1][0] = 0;  Z[1][1] = f1; Z[1][2] = 0;  Z[1][3] = -f1 * rz; Z[1][4] = 0;        Z[1][5] = f1 * rx;
@@ -258,6 +260,7 @@ Grid grid_of(const fcvm_ctx *c) {
     g.h[d] = c->dh[d];
   }
   g.scale = c->dscale;
+  g.active = c->cl_active;
   return g;
 }
 
@@ -272,7 +275,7 @@ int dalloc2(T **p, int64_t n) {
 }  // namespace
 
 extern "C" int fcvm_set_deflation(fcvm_ctx *c, int ncx, int ncy, int ncz, const int32_t *cid, const double *lo,
-                                  const double *h) {
+                                  const double *h, const uint8_t *active) {
   FCVM_CHECK(c && c->nn > 0, FCVM_E_ARG, "fcvm_set_deflation: call fcvm_set_mesh first");
   c->defl_ready = c->defl_structure = false;
   if (ncx <= 0 || ncy <= 0 || ncz <= 0 || !cid) {          // switch off
@@ -299,6 +302,11 @@ extern "C" int fcvm_set_deflation(fcvm_ctx *c, int ncx, int ncy, int ncz, const 
     for (int64_t i = 0; i < nn; i++) nodes[(size_t)fill[(size_t)cid[i]]++] = (int32_t)i;
   }
   FCVM_TRY(dalloc2(&c->d_cid, nn)); FCVM_TRY(dalloc2(&c->cl_ptr, ncl + 1)); FCVM_TRY(dalloc2(&c->cl_nodes, nn));
+  FCVM_TRY(dalloc2(&c->cl_active, ncl));
+  if (active)
+    FCVM_CUDA(cudaMemcpy(c->cl_active, active, (size_t)ncl, cudaMemcpyHostToDevice));
+  else
+    FCVM_CUDA(cudaMemset(c->cl_active, 1, (size_t)ncl));
   FCVM_CUDA(cudaMemcpy(c->d_cid, cid, sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
   FCVM_CUDA(cudaMemcpy(c->cl_ptr, ptr.data(), sizeof(int32_t) * (ncl + 1), cudaMemcpyHostToDevice));
   FCVM_CUDA(cudaMemcpy(c->cl_nodes, nodes.data(), sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
@@ -428,6 +436,7 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
 }
 
 void deflation_free(fcvm_ctx *c) {
+  cudaFree(c->cl_active); c->cl_active = nullptr;
   cudaFree(c->d_cid); cudaFree(c->cl_ptr); cudaFree(c->cl_nodes); cudaFree(c->kz_rel); cudaFree(c->kz_val);
   cudaFree(c->ent_ptr); cudaFree(c->ent); cudaFree(c->ent_inv); c->ent_inv = nullptr; cudaFree(c->dE); cudaFree(c->dEinv); cudaFree(c->d_rhs); cudaFree(c->d_lam);
   cudaFree(c->spmv_part2);

@@ -119,7 +119,7 @@ class Engine:
         cluster); ``grid=(ncx, ncy, ncz)`` overrides the automatic choice; ``target_unknowns=0``
         switches it off.  Takes effect at the next ``assemble``.  Returns the grid used."""
         if not target_unknowns and grid is None:
-            call("fcvm_set_deflation", self._ctx, 0, 0, 0, None, None, None)
+            call("fcvm_set_deflation", self._ctx, 0, 0, 0, None, None, None, None)
             self.deflation_grid = None
             return None
         xyz, el = self._nocoord, self._elNodes
@@ -133,9 +133,20 @@ class Engine:
         grid, h = deflation_boxes(lo, hi, ext, target_unknowns, grid)
         ijk = np.minimum(((xyz - lo) / h).astype(np.int64), grid - 1)
         cid = np.ascontiguousarray(ijk[:, 0] + grid[0] * (ijk[:, 1] + grid[1] * ijk[:, 2]), dtype=np.int32)
+        # a box needs a handful of nodes with all three dofs free for its six modes to be independent
+        # (otherwise the dense coarse matrix is singular); boxes below that carry no modes
+        free_node = (self.fixmask.reshape(-1, 3) == 0).all(axis=1) if getattr(self, "fixmask", None) is not None \
+            else np.ones(self.nn, dtype=bool)
+        if self.comm is not None and self.comm.world > 1:
+            free_node = free_node & (self.comm.part.multiplicity[self.comm.part.nodes[self.comm.rank]] == 1)
+        count = np.bincount(cid[free_node], minlength=int(np.prod(grid))).astype(np.int64)
+        if self.comm is not None and self.comm.world > 1:
+            count = np.sum(self.comm.allgather(count), axis=0)
+        active = np.ascontiguousarray(count >= 8, dtype=np.uint8)
         lo_c, h_c = _np(lo, np.float64), _np(h, np.float64)
         call("fcvm_set_deflation", self._ctx, int(grid[0]), int(grid[1]), int(grid[2]),
-             cid.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _ptr(lo_c, f64p), _ptr(h_c, f64p))
+             cid.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _ptr(lo_c, f64p), _ptr(h_c, f64p), _ptr(active, u8p))
+        self.deflation_active_boxes = int(active.sum())
         self.deflation_grid = tuple(int(g) for g in grid)
         return self.deflation_grid
 

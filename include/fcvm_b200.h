@@ -146,9 +146,10 @@ int fcvm_pcg_solve(fcvm_ctx *ctx, const double *b, double *x, double rtol, int m
  * The clusters form an ncx x ncy x ncz grid of boxes lo + (i,j,k)*h over the (global) bounding box;
  * cid[n] = ix + ncx*(iy + ncy*iz) is the box of local node n.  A box must be at least two elements
  * wide in every direction (a node then couples to at most 2 x 2 x 2 boxes).  Takes effect at the next fcvm_assemble (K Z and (Z^T K Z)^-1 are built
- * there); ncx = 0 switches it off.  6*ncx*ncy*ncz <= 16384. */
+ * there); ncx = 0 switches it off.  6*ncx*ncy*ncz <= 16384.  active[box] = 0 (optional, NULL = all 1)
+ * drops the modes of a box that holds too few free nodes for six independent rigid-body modes. */
 int fcvm_set_deflation(fcvm_ctx *ctx, int ncx, int ncy, int ncz, const int32_t *cid, const double *lo,
-                       const double *h);
+                       const double *h, const uint8_t *active);
 
 /* ---- stress update: update_stress_load (fcVM.py:2196-2464) ---------------------------------- */
 /* Reads SIG_OLD / SIG_YIELD, writes SIG_NEW / SIG_TEST / PGP, and qin = internal force vector
