@@ -279,9 +279,20 @@ def main():
         print(json.dumps(line))
         return 0
 
+    if a.gpus > 1 and world == 1 and "WORLD_SIZE" not in os.environ:
+        # started as plain `python bench.py --gpus N`: launch the ranks the way the driver does
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    if a.gpus != world:
+        raise SystemExit(f"bench.py: --gpus {a.gpus} but WORLD_SIZE is {world}")
     from fcvm_workbench_b200 import fcVM
     from fcvm_workbench_b200.hostpath import HostEngine
     torch.cuda.set_device(local)
