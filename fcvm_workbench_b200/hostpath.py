@@ -111,37 +111,65 @@ class HostEngine:
     def copy(self, x, y, n=None):
         y[:] = x
 
+    # in-place forms without temporaries: a fresh 33 MB numpy temporary costs more in page faults than
+    # the arithmetic on it
+    def _tmp(self, like):
+        t = getattr(self, "_scratch", None)
+        if t is None or t.shape != like.shape:
+            t = self._scratch = np.empty_like(like)
+        return t
+
     def axpby(self, a, x, b, y, n=None):
+        """y = a*x + b*y"""
         if b == 0.0:
             np.multiply(x, a, out=y)
-        else:
+        elif a == 0.0:
             y *= b
-            y += a * x
+        else:
+            t = self._tmp(x)
+            np.multiply(x, a, out=t)
+            if b != 1.0:
+                y *= b
+            y += t
 
     def axpbypcz(self, a, x, b, y, c, z, n=None):
-        t = a * x + b * y
+        """z = a*x + b*y + c*z"""
+        t = self._tmp(x)
         if c == 0.0:
-            z[:] = t
+            np.multiply(x, a, out=z)
         else:
-            z *= c
-            z += t
+            if c != 1.0:
+                z *= c
+            if a == 1.0:
+                z += x
+            else:
+                np.multiply(x, a, out=t)
+                z += t
+        np.multiply(y, b, out=t)
+        z += t
 
     def _gsum(self, v: float) -> float:
         return float(v) if self._w is None else float(sum(self.comm.allgather(float(v))))
 
     def dot(self, x, y, n=None):
-        return self._gsum(np.dot(x, y) if self._w is None else np.dot(self._w * x, y))
+        if self._w is None:
+            return float(np.dot(x, y))
+        t = self._tmp(x)
+        np.multiply(self._w, x, out=t)
+        return self._gsum(np.dot(t, y))
 
     def norm(self, x):
         return float(np.sqrt(self.dot(x, x)))
 
     def residual(self, lbd, glv, qin, r):
-        r[:] = self._nodal[_fc.FIXDOF] * (lbd * glv - qin)
+        np.multiply(glv, lbd, out=r)
+        r -= qin
+        r *= self._nodal[_fc.FIXDOF]
         return self.norm(r)
 
     def masked_norm(self, x, mask_host):
         t = x * np.asarray(mask_host, dtype=np.float64)
-        return float(np.sqrt(self.dot(t, t)))
+        return float(np.sqrt(self._gsum(np.dot(t, t) if self._w is None else np.dot(self._w * t, t))))
 
     def max_node_disp(self, disp):
         nodes = (self.ndof - 1) // 3 if self._un_nodes is None else self._un_nodes      # fcVM.py:1494-1497

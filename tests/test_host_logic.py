@@ -127,3 +127,29 @@ def test_deflation_box_grid():
     # explicit grid is clipped by the same rules
     g, _ = deflation_boxes([0, 0, 0], [10, 10, 10], [1, 1, 1], grid=(8, 8, 8))
     assert tuple(g) == (4, 4, 4)
+
+
+def test_host_engine_vector_algebra_is_in_place_and_exact():
+    """hostpath.HostEngine's numpy algebra (the reference's vector algebra between the heavy calls)."""
+    from fcvm_workbench_b200 import hostpath
+    H = hostpath.HostEngine.__new__(hostpath.HostEngine)          # no GPU: only the host-side methods
+    H._w, H.comm = None, None
+    rng = np.random.default_rng(0)
+    H._nodal = {hostpath._fc.FIXDOF: (rng.random(1000) > 0.2).astype(float)}
+    for a, b in ((2.0, 0.0), (0.0, 0.5), (1.5, 1.0), (1.5, -0.3)):
+        x, y = rng.normal(size=1000), rng.normal(size=1000)
+        ref = a * x + b * y
+        H.axpby(a, x, b, y)
+        assert np.allclose(y, ref, rtol=0, atol=1e-15)
+    for a, b, c in ((1.0, 0.7, 1.0), (2.0, 0.7, 0.0), (0.25, -0.25, 0.0), (1.5, 2.5, 0.5)):
+        x, y, z = (rng.normal(size=1000) for _ in range(3))
+        ref = a * x + b * y + c * z
+        H.axpbypcz(a, x, b, y, c, z)
+        assert np.allclose(z, ref, rtol=0, atol=1e-14)
+    glv, qin, r = (rng.normal(size=1000) for _ in range(3))
+    ref = H._nodal[hostpath._fc.FIXDOF] * (1.3 * glv - qin)
+    n = H.residual(1.3, glv, qin, r)
+    assert np.allclose(r, ref, rtol=0, atol=1e-15) and abs(n - np.linalg.norm(ref)) < 1e-12
+    d = rng.normal(size=3 * 7)
+    H.ndof, H._un_nodes = 21, None
+    assert H.max_node_disp(d) == pytest.approx(np.sqrt((d[:18].reshape(-1, 3) ** 2).sum(axis=1).max()))   # last node left out
