@@ -217,13 +217,13 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
   }
 }
 
-// lam = Einv rhs: one warp per row, fixed order
+// lam = Einv rhs for rows [row0, row1): one warp per row, fixed order
 __global__ void __launch_bounds__(256)
-k_gemv(int64_t n, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ y,
-       const double *__restrict__ sc, int done_slot) {
+k_gemv(int64_t n, int64_t row0, int64_t row1, const double *__restrict__ A, const double *__restrict__ x,
+       double *__restrict__ y, const double *__restrict__ sc, int done_slot) {
   if (sc && sc[done_slot] >= 0.0) return;
-  const int64_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= n) return;
+  const int64_t row = row0 + blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= row1) return;
   const int lane = threadIdx.x & 31;
   double s = 0.0;
   for (int64_t q = lane; q < n; q += 32) s += A[row * n + q] * x[q];
@@ -427,8 +427,17 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
   const int64_t n6 = 6 * c->ncl;
   k_coarse_rhs<<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val, c->nent, c->xyz, fixdof,
                                                 c->dof_weight, r, y, c->d_rhs, sc, done_slot);
-  if (c->world > 1) FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_rhs, n6));
-  k_gemv<<<grid_for(n6, 8), 256, 0, st>>>(n6, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
+  if (c->world > 1) {
+    // every rank holds E^-1; each applies its own share of the rows and the shares are put together by an
+    // all-reduce over a vector that is zero elsewhere (exact: x + 0 = x, so lam is identical on all ranks)
+    FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_rhs, n6));
+    const int64_t row0 = n6 * c->rank / c->world, row1 = n6 * (c->rank + 1) / c->world;
+    FCVM_CUDA(cudaMemsetAsync(c->d_lam, 0, sizeof(double) * n6, st));
+    k_gemv<<<grid_for(row1 - row0, 8), 256, 0, st>>>(n6, row0, row1, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
+    FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_lam, n6));
+  } else {
+    k_gemv<<<grid_for(n6, 8), 256, 0, st>>>(n6, 0, n6, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
+  }
   k_expand<<<grid_for(c->nn, 256), 256, 0, st>>>(c->nn, g, c->d_cid, c->xyz, fixdof, c->d_lam, base, out, sc, done_slot);
   c->launches += 3;
   FCVM_CUDA(cudaGetLastError());
