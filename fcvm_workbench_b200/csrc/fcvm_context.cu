@@ -588,6 +588,9 @@ extern "C" int fcvm_set_constraints(fcvm_ctx *c, const uint8_t *fixmask, const d
   FCVM_CUDA(cudaMemcpy(c->buf[FCVM_BUF_FIXDOF], fixdof.data(), sizeof(double) * n3, cudaMemcpyHostToDevice));
   c->have_bcs = true;
   c->assembled = false;
+  // the sparsity of K Z (which blocks vanish) depends on the prescribed dofs: rebuilt at the next assembly
+  c->defl_structure = false;
+  c->defl_ready = false;
   return FCVM_OK;
 }
 
