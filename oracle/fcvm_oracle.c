@@ -367,8 +367,7 @@ int64_t fcvm_oracle_calc_gsm(int64_t ne, int64_t nn, const int64_t *elNodes, con
 
 /* ---- fcVM.py:819-1079 (calcTSM), nstep > 1 branch: consistent tangent -------
  * D - pmat at plastic Gauss points (fcVM.py:983-1000), geometry updated with
- * disp_new (fcVM.py:962-967).  The linear-buckling branch (nstep == 1, geometric
- * stiffness nsm) is outside the hot path and not restated. */
+ * disp_new (fcVM.py:962-967).  The linear-buckling branch (nstep == 1) follows below. */
 int64_t fcvm_oracle_calc_tsm(int64_t ne, int64_t nn, const int64_t *elNodes, const double *nocoord, double E,
                              double nu, double density, const uint8_t *fixmask, const double *fixval, double grav_x,
                              double grav_y, double grav_z, const double *disp_new, const double *sig_old,
@@ -434,6 +433,82 @@ int64_t fcvm_oracle_calc_tsm(int64_t ne, int64_t nn, const int64_t *elNodes, con
     emit_coo((const double(*)[30])esm, dof, fixmask, fixval, row, col, stm, modf, &pos);
   }
   free(esm);
+  return pos;
+}
+
+/* ---- fcVM.py:819-1079 (calcTSM), nstep == 1 branch: linear buckling ----------
+ * Material stiffness esm (D, or D - pmat at plastic points) and geometric stiffness
+ * nsm = sum_gp w|J| GM^T SM GM with GM = kron(dshpg, I3), SM = kron(sig, I3)
+ * (fcVM.py:1002-1006) on the undeformed geometry; the full 30 x 30 element matrices go
+ * out as COO triplets, rows and columns of prescribed dofs are kept and their diagonal
+ * is stiffened by 100 (fcVM.py:1052-1062).  row/col/stms/stmg need 900*ne entries. */
+int64_t fcvm_oracle_calc_tsm_buckling(int64_t ne, const int64_t *elNodes, const double *nocoord, double E, double nu,
+                                      const uint8_t *fixmask, const double *sig_old, const uint8_t *pgp, double Et_E,
+                                      int64_t *row, int64_t *col, double *stms, double *stmg) {
+  double dmat[6][6], dp[6][6], bmatV[6][30], dshpg[3][10], xlv[10][3];
+  double(*esm)[30] = malloc(sizeof(double) * 900);
+  double(*nsm)[30] = malloc(sizeof(double) * 900);
+  int64_t dof[30];
+  int64_t pos = 0;
+  memset(bmatV, 0, sizeof(bmatV));
+  hooke(E, nu, dmat);
+  double G = E / (1.0 + nu) / 2.0;
+  if (Et_E > 0.95) Et_E = 0.95;
+  double Et = Et_E * E;
+  double H = Et / (1.0 - Et_E);
+  for (int64_t el = 0; el < ne; el++) {
+    const int64_t *nodes = elNodes + 10 * el;
+    memset(esm, 0, sizeof(double) * 900);
+    memset(nsm, 0, sizeof(double) * 900);
+    for (int j = 0; j < 10; j++)
+      for (int i = 0; i < 3; i++) xlv[j][i] = nocoord[3 * (nodes[j] - 1) + i];
+    for (int ip = 0; ip < 4; ip++) {
+      int64_t ip4 = 4 * el + ip, ip24 = 24 * el + 6 * ip;
+      double xi = GP10[ip][0], et = GP10[ip][1], ze = GP10[ip][2], w = GP10[ip][3];
+      double xsj = dshp10tet(xi, et, ze, xlv, bmatV, dshpg);
+      const double *s0 = sig_old + ip24;
+      if (pgp[ip4]) {
+        double s[6];
+        for (int c = 0; c < 6; c++) s[c] = s0[c];
+        double p = (s[0] + s[1] + s[2]) / 3.0;
+        s[0] -= p;
+        s[1] -= p;
+        s[2] -= p;
+        double svm = sqrt(1.5 * (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) +
+                          3.0 * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5]));
+        if (svm == 0.0) svm = 1.0;
+        double fac = 3.0 * G / (1.0 + H / 3.0 / G) / (svm * svm);
+        for (int i1 = 0; i1 < 6; i1++)
+          for (int i2 = 0; i2 < 6; i2++) dp[i1][i2] = dmat[i1][i2] - fac * s[i1] * s[i2];
+        add_btdb(esm, bmatV, dp, w * fabs(xsj));
+      } else {
+        add_btdb(esm, bmatV, dmat, w * fabs(xsj));
+      }
+      /* sig as a 3 x 3 tensor (Voigt order xx yy zz xy zx yz, fcVM.py:970-972) */
+      const double sg[3][3] = {{s0[0], s0[3], s0[4]}, {s0[3], s0[1], s0[5]}, {s0[4], s0[5], s0[2]}};
+      for (int a = 0; a < 10; a++)
+        for (int b = 0; b < 10; b++) {
+          double v = 0.0;
+          for (int m = 0; m < 3; m++)
+            for (int n = 0; n < 3; n++) v += dshpg[m][a] * sg[m][n] * dshpg[n][b];
+          v *= w * fabs(xsj);
+          for (int i = 0; i < 3; i++) nsm[3 * a + i][3 * b + i] += v;
+        }
+    }
+    for (int i = 0; i < 10; i++)
+      for (int j = 0; j < 3; j++) dof[3 * i + j] = 3 * (nodes[i] - 1) + j;
+    for (int i = 0; i < 30; i++)
+      for (int j = 0; j < 30; j++) {
+        row[pos] = dof[i];
+        col[pos] = dof[j];
+        stms[pos] = esm[i][j];
+        stmg[pos] = nsm[i][j];
+        if (i == j && fixmask[dof[i]]) stms[pos] *= 100.0;
+        pos++;
+      }
+  }
+  free(esm);
+  free(nsm);
   return pos;
 }
 

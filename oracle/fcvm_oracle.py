@@ -131,14 +131,23 @@ def calcGSM(elNodes, nocoord, materialbyElement, fix, grav_x, grav_y, grav_z, lo
 def calcTSM(nstep, elNodes, nocoord, materialbyElement, fix, grav_x, grav_y, grav_z, loadfaces, pressure,
             loadvertices, vertexloads, loadedges, edgeloads, loadfaces_uni, faceloads, disp_new, du, sig_old, pgp,
             Et_E, return_esm=False):
-    """fcVM.py:819-1079, ``nstep > 1`` branch (consistent tangent on updated geometry)."""
-    if not float(nstep) > 1.0:
-        raise NotImplementedError("linear-buckling branch of calcTSM is outside the restated path")
+    """fcVM.py:819-1079: ``nstep > 1`` consistent tangent on the updated geometry; ``nstep == 1`` material and
+    geometric stiffness of the linear-buckling analysis (returned as stms, stmg with full-matrix row/col)."""
     elNodes = _c(elNodes, np.int64)
     nocoord = _c(nocoord, np.float64)
     ne, nn = len(elNodes), len(nocoord)
     E, nu, rho = _material(materialbyElement)
     mask, val = _fix_dense(fix, 3 * nn)
+    if not float(nstep) > 1.0:
+        n9 = 900 * ne
+        row, col = np.zeros(n9, dtype=np.int64), np.zeros(n9, dtype=np.int64)
+        stms, stmg = np.zeros(n9), np.zeros(n9)
+        lib().fcvm_oracle_calc_tsm_buckling.restype = ctypes.c_int64
+        pos = lib().fcvm_oracle_calc_tsm_buckling(
+            ctypes.c_int64(ne), _p(elNodes, _i64p), _p(nocoord, _f64p), ctypes.c_double(E), ctypes.c_double(nu),
+            _p(mask, _u8p), _p(_c(sig_old, np.float64), _f64p), _p(_c(pgp, np.uint8), _u8p), ctypes.c_double(Et_E),
+            _p(row, _i64p), _p(col, _i64p), _p(stms, _f64p), _p(stmg, _f64p))
+        return None, stms[:pos], stmg[:pos], row[:pos], col[:pos], None, None
     disp_new = _c(disp_new, np.float64)
     glv = load_vector(nocoord, loadfaces, pressure, loadvertices, vertexloads, loadedges, edgeloads,
                       loadfaces_uni, faceloads, disp=disp_new)
@@ -257,10 +266,9 @@ def calcDisp(model, ctl, clicks=(), factorize: Optional[Callable] = None, log: O
         relax = 1.0
         disp_output = "total"
         scale_up = 1.1
-        if not (float(nstep) > 1.0 and maxImp == 0.0):
-            raise NotImplementedError("eigen-buckling pre-analysis (GNLY with imperfection) is outside the hot path")
     else:
         LD = False
+    eigenval, eigenvec = np.zeros(2), None
 
     ndof = len(glv)
     nelem = len(elNodes)
@@ -309,8 +317,48 @@ def calcDisp(model, ctl, clicks=(), factorize: Optional[Callable] = None, log: O
     update_stress_load(gp10, elNodes, nocoord, mat, 1.0e6 * sig_yield, np.zeros(ndof), ue, sig_old, sig_new,
                        sig_test, np.zeros(ndof), Et_E, False, pgp)          # fcVM.py:1195-1197
 
+    if LD and not (float(nstep) > 1.0 and maxImp == 0.0):    # linear buckling analysis, fcVM.py:1199-1214
+        from scipy.sparse.linalg import eigsh
+        _, stms, stmg, brow, bcol, _, _ = calcTSM(1.0, elNodes, nocoord, mat, fix, ctl.grav_x, ctl.grav_y, ctl.grav_z,
+                                                  m.loadfaces, m.pressure, m.loadvertices, m.vertexloads, m.loadedges,
+                                                  m.edgeloads, m.loadfaces_uni, m.faceloads, np.zeros(ndof),
+                                                  np.zeros(ndof), sig_new, pgp, Et_E)
+        Kb = scsp.csc_matrix((stms, (brow, bcol)), shape=(ndof, ndof))
+        Gb = -scsp.csc_matrix((stmg, (brow, bcol)), shape=(ndof, ndof))
+        eigenval, eigenvec = eigsh(Kb, k=2, M=Gb, sigma=0.1, which="LM", mode="buckling")
+        say(f"buckling load factors: {eigenval}")
+
     iterat_tot = 0
     mrr = False
+    if float(nstep) != 1.0 and LD and maxImp != 0.0:         # imperfection and restart, fcVM.py:1224-1294
+        ev1, ev2 = float(ctl.ev1), float(ctl.ev2)
+        ua = ev1 / (ev1 + ev2) * eigenvec[:, 0] + ev2 / (ev1 + ev2) * eigenvec[:, 1]
+        ub = ev1 / (ev1 + ev2) * eigenvec[:, 0] - ev2 / (ev1 + ev2) * eigenvec[:, 1]
+        ma, mb = np.max(np.abs(ua)), np.max(np.abs(ub))
+        if ma > mb:
+            imax = np.argmax(np.abs(ua))
+            imper = maxImp / ma * np.sign(ua[imax]) * ua
+        else:
+            imax = np.argmax(np.abs(ub))
+            imper = maxImp / mb * np.sign(ub[imax]) * ub
+        nocoord += imper.reshape(-1, 3)
+        (stm, row, col, glv, modf, *_rest) = calcGSM(
+            elNodes, nocoord, mat, fix, ctl.grav_x, ctl.grav_y, ctl.grav_z, m.loadfaces, m.pressure, m.loadvertices,
+            m.vertexloads, m.loadedges, m.edgeloads, m.loadfaces_uni, m.faceloads)
+        gsm = lower_csc(stm, row, col, ndof)
+        qnorm = np.linalg.norm(glv)
+        if qnorm < 1.0:
+            qnorm = 1.0
+        factor = factorize(gsm)
+        f = fixdof * glv + modf
+        ue = factor(f)
+        disp_el = ue.copy()
+        dl0 = 1.0 / nstep
+        dl = dl0
+        du = dl * ue
+        sig_old, sig_test = z24(), z24()
+        disp_new, disp_old = np.zeros(ndof), np.zeros(ndof)
+        lbd = np.zeros(1)
     if float(nstep) == 1.0:                                  # elastic analysis, fcVM.py:1216-1223
         disp_new = ue
         lbd = np.append(lbd, 1.0)
@@ -485,4 +533,5 @@ def calcDisp(model, ctl, clicks=(), factorize: Optional[Callable] = None, log: O
                 ecrplot=np.asarray(ecrplot), csrplot=np.asarray(csrplot), fail=fail, nocoord_old=nocoord_old,
                 lbd=np.asarray(lbd), iters=np.asarray(iters), nplastic=np.asarray(nplastic), iterat_tot=iterat_tot,
                 glv=glv, modf=modf, x=x, V=V, loadsum=(lsx, lsy, lsz), sig_yield=sig_yield, pgp=pgp,
+                eigenval=eigenval, eigenvec=eigenvec,
                 sig_test=sig_test, stm=stm, row=row, col=col)

@@ -18,6 +18,7 @@ Fixtures
 ``cube2_force``    48-element block, traction + gravity, hardening, "add" click.
 ``cube2_gnly``     large-displacement branch (calcTSM every iteration).
 ``cube2_elastic``  nstep = 1: the linear-elastic analysis (no load stepping).
+``column_buckling`` GNLY with imperfection: linear buckling (eigsh), imperfect geometry, restart.
 ``kernels``        single calls of calcGSM (element matrices), update_stress_load
                    (LD off/on), update_PEEQ_CSR and mapStresses on a distorted mesh
                    with random state.
@@ -59,13 +60,15 @@ def clicks_field(clicks):
     return np.array([f"{e[0]}:{e[1]}" if isinstance(e, tuple) else e for e in clicks] or [""], dtype="U32")
 
 
-def analysis_case(name, m, c, clicks=()):
+def analysis_case(name, m, c, clicks=(), extra=()):
     d = rh.run_reference(m, c, clicks=clicks)
     out = dict(model_fields(m))
     out.update(ctl_fields(c))
     out["clicks"] = clicks_field(clicks)
     for k in ("lout", "un", "crip", "peeqplot", "pplot", "svmplot", "triaxplot", "ecrplot", "csrplot",
               "displacements", "disp_el", "stresses", "peeq", "sigmises", "csr", "glv", "modf", "x"):
+        out["r_" + k] = np.asarray(d[k])
+    for k in extra:
         out["r_" + k] = np.asarray(d[k])
     out["r_iters"] = np.asarray(d["iters"], dtype=np.int64)
     out["r_V"] = np.array(d["V"])
@@ -165,7 +168,18 @@ def main():
     analysis_case("cube2_gnly", cube_model(2, mode="platen", top_disp=0.4),
                   Control(sig_yield=240.0, nstep=6, error_max=1e-6, target_LF=2.0, Et_E=0.02, gnl="GNLY"))
     elastic_case()
+    buckling_case()
     kernel_case()
+
+
+def buckling_case():
+    """GNLY with an imperfection: linear buckling analysis (calcTSM nstep = 1, eigsh), imperfect geometry,
+    restart and large-displacement load stepping (fcVM.py:1199-1294).  Pins the oracle's restatement of that
+    branch; the CUDA path does not cover it yet."""
+    m = cube_model(2, mode="platen", top_disp=-0.4, nxyz=(1, 1, 4), size=2.0)
+    c = Control(sig_yield=240.0, nstep=4, error_max=1e-6, target_LF=1.0, Et_E=0.02, gnl="GNLY", maxImp="0.05",
+                ev1="1.0", ev2="0.0")
+    analysis_case("column_buckling", m, c, extra=("eigenval",))
 
 
 def elastic_case():
