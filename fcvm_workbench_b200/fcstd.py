@@ -143,7 +143,18 @@ class _BoxShape:
         a = [self.ext[i] for i in range(3) if i != axis]
         return a[0] * a[1]
 
+    def vertex(self, sub: str):
+        """Vertex1..Vertex8 of a box: x from bit 2, y from bit 1 of (number - 1), z = height when bit 0 is
+        clear (Vertex1 = (0, 0, H), Vertex2 = (0, 0, 0), Vertex4 = (0, W, 0), Vertex6 = (L, 0, 0) -- the
+        coordinates FreeCAD stores with the constraints of VM_Uniaxial_Tension_Example.FCStd)."""
+        k = int(sub[6:]) - 1
+        return np.array([self.ext[0] if k & 4 else 0.0, self.ext[1] if k & 2 else 0.0, 0.0 if k & 1 else self.ext[2]])
+
     def nodes_on(self, sub: str, coords: np.ndarray, tol: float) -> np.ndarray:
+        if sub.startswith("Vertex"):
+            return np.nonzero(np.linalg.norm(coords - self.vertex(sub), axis=1) <= tol)[0]
+        if not sub.startswith("Face"):
+            raise NotImplementedError(f"'{sub}': only faces and vertices of a Part::Box are resolved headlessly")
         axis, val = self.face(sub)
         return np.nonzero(np.abs(coords[:, axis] - val) <= tol)[0]
 
@@ -222,8 +233,6 @@ def read_fcstd(path: str) -> Model:
                 vals = [_float(o, "xDisplacement"), _float(o, "yDisplacement"), _float(o, "zDisplacement")]
             bc = []
             for obj_name, sub in _refs(o):
-                if not sub.startswith("Face"):
-                    raise NotImplementedError("only face references are resolved headlessly")
                 bc.extend((shape_of(obj_name).nodes_on(sub, nocoord, tol) + 1).tolist())
             bc = list(dict.fromkeys(bc))
             if bc:

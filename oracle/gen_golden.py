@@ -17,6 +17,7 @@ Fixtures
 ``cube2_platen``   48-element block, displacement control, hardening, one restart.
 ``cube2_force``    48-element block, traction + gravity, hardening, "add" click.
 ``cube2_gnly``     large-displacement branch (calcTSM every iteration).
+``vm_uniaxial_tension`` the reference's VM_Uniaxial_Tension_Example (BASELINE config 0) with its control file.
 ``cube2_elastic``  nstep = 1: the linear-elastic analysis (no load stepping).
 ``column_buckling`` GNLY with imperfection: linear buckling (eigsh), imperfect geometry, restart.
 ``kernels``        single calls of calcGSM (element matrices), update_stress_load
@@ -168,8 +169,17 @@ def main():
     analysis_case("cube2_gnly", cube_model(2, mode="platen", top_disp=0.4),
                   Control(sig_yield=240.0, nstep=6, error_max=1e-6, target_LF=2.0, Et_E=0.02, gnl="GNLY"))
     elastic_case()
+    uniaxial_case()
     buckling_case()
     kernel_case()
+
+
+def uniaxial_case():
+    """BASELINE config 0: the reference's VM_Uniaxial_Tension_Example (FCStd + control file), continued past
+    first yield with one "add" click (plateau at load factor 10 = yield stress / applied pressure)."""
+    m = read_fcstd(os.path.join(rh.REFERENCE_ROOT, "freeCAD files", "VM_Uniaxial_Tension_Example.FCStd"))
+    c = read_control(os.path.join(rh.REFERENCE_ROOT, "control files", "VM_Uniaxial_Tension_Example.inp"))
+    analysis_case("vm_uniaxial_tension", m, c, clicks=[("add", 10.5)])
 
 
 def buckling_case():

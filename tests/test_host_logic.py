@@ -153,3 +153,22 @@ def test_host_engine_vector_algebra_is_in_place_and_exact():
     d = rng.normal(size=3 * 7)
     H.ndof, H._un_nodes = 21, None
     assert H.max_node_disp(d) == pytest.approx(np.sqrt((d[:18].reshape(-1, 3) ** 2).sum(axis=1).max()))   # last node left out
+
+
+def test_fcstd_reader_resolves_box_vertices_of_the_uniaxial_example():
+    """BASELINE config 0: constraints on Vertex2 / Vertex4 / Vertex6 of a Part::Box and pressures on all faces."""
+    path = "/root/reference/freeCAD files/VM_Uniaxial_Tension_Example.FCStd"
+    if not os.path.isfile(path):
+        pytest.skip("reference models not present on this machine")
+    from fcvm_workbench_b200.fcstd import read_fcstd, _BoxShape
+    m = read_fcstd(path)
+    z = load("vm_uniaxial_tension")
+    assert np.array_equal(m.elNodes, z["m_elNodes"]) and np.allclose(m.nocoord, z["m_nocoord"])
+    # statically determinate support: origin fully fixed, (0,10,0) in x and z, (10,0,0) in z
+    at = lambda p: int(np.nonzero(np.linalg.norm(m.nocoord - np.array(p), axis=1) < 1e-9)[0][0])
+    o, a, b = at((0, 0, 0)), at((0, 10, 0)), at((10, 0, 0))
+    assert sorted(m.fix) == sorted([3 * o, 3 * o + 1, 3 * o + 2, 3 * a, 3 * a + 2, 3 * b + 2])
+    assert len(m.loadfaces) - 1 == 24 and set(np.round(m.pressure[1:], 6)) == {0.0, 10.0}
+    box = _BoxShape(10.0, 10.0, 10.0)
+    assert list(box.vertex("Vertex2")) == [0, 0, 0] and list(box.vertex("Vertex4")) == [0, 10, 0]
+    assert list(box.vertex("Vertex6")) == [10, 0, 0] and list(box.vertex("Vertex1")) == [0, 0, 10]
