@@ -18,6 +18,7 @@ Fixtures
 ``cube2_force``    48-element block, traction + gravity, hardening, "add" click.
 ``cube2_gnly``     large-displacement branch (calcTSM every iteration).
 ``vm_uniaxial_tension`` the reference's VM_Uniaxial_Tension_Example (BASELINE config 0) with its control file.
+``simple_shear``   the reference's Simple Shear model with its control file.
 ``cube2_elastic``  nstep = 1: the linear-elastic analysis (no load stepping).
 ``column_buckling`` GNLY with imperfection: linear buckling (eigsh), imperfect geometry, restart.
 ``kernels``        single calls of calcGSM (element matrices), update_stress_load
@@ -170,6 +171,7 @@ def main():
                   Control(sig_yield=240.0, nstep=6, error_max=1e-6, target_LF=2.0, Et_E=0.02, gnl="GNLY"))
     elastic_case()
     uniaxial_case()
+    simple_shear_case()
     buckling_case()
     kernel_case()
 
@@ -180,6 +182,14 @@ def uniaxial_case():
     m = read_fcstd(os.path.join(rh.REFERENCE_ROOT, "freeCAD files", "VM_Uniaxial_Tension_Example.FCStd"))
     c = read_control(os.path.join(rh.REFERENCE_ROOT, "control files", "VM_Uniaxial_Tension_Example.inp"))
     analysis_case("vm_uniaxial_tension", m, c, clicks=[("add", 10.5)])
+
+
+def simple_shear_case():
+    """The reference's ``Simple Shear`` model with its control file (force-controlled shear, 96 Gauss points
+    plastic at the end)."""
+    m = read_fcstd(os.path.join(rh.REFERENCE_ROOT, "freeCAD files", "Simple Shear.FCStd"))
+    c = read_control(os.path.join(rh.REFERENCE_ROOT, "control files", "Simple Shear.inp"))
+    analysis_case("simple_shear", m, c)
 
 
 def buckling_case():
