@@ -132,3 +132,32 @@ def test_interface_sum_and_dots_over_gloo_world2(oracle, tmp_path):
     ia = np.isin(part.nodes[0], part.if_nodes)
     ib = np.isin(part.nodes[1], part.if_nodes)
     assert np.array_equal(a.reshape(-1, 3)[ia], b.reshape(-1, 3)[ib])                 # bit-identical on both ranks
+
+
+def test_scattered_partition_with_many_ranks_per_node(oracle):
+    """Element order shuffled, so every rank's elements are scattered through the mesh and many nodes are
+    shared by three and more ranks: the interface maps and weights must still complete every sum."""
+    m, du = _case()
+    rng = np.random.default_rng(9)
+    perm = rng.permutation(m.ne)
+    import dataclasses
+    ms = dataclasses.replace(m, elNodes=m.elNodes[perm], materialbyElement=m.materialbyElement[perm])
+    world = 4
+    part = slab_partition(ms, world)
+    assert part.multiplicity.max() >= 3
+    ref = _local_q(oracle, ms, du)[2]
+    q = np.zeros((m.nn, 3))
+    wsum = np.zeros(m.nn)
+    dot = 0.0
+    for r in range(world):
+        lm = part.local_model(r)
+        g = part.nodes[r]
+        dofs = (3 * g[:, None] + np.arange(3)).ravel()
+        q[g] += _local_q(oracle, lm, du[dofs])[2].reshape(-1, 3)
+        w, loc, slot = part.interface(r)
+        wsum[g] += w[::3]
+        dot += float(np.dot(w * ref[dofs], ref[dofs]))
+        assert np.array_equal(part.if_nodes[slot], g[loc])
+    assert np.allclose(wsum, 1.0, rtol=0, atol=1e-15)
+    assert np.abs(q.ravel() - ref).max() < 1e-12 * np.abs(ref).max()
+    assert abs(dot - np.dot(ref, ref)) < 1e-12 * np.dot(ref, ref)
