@@ -20,6 +20,7 @@
 using namespace fcvm;
 
 extern "C" int fcvm_comm_allreduce_sum(fcvm_ctx *c, double *dev, int64_t n);
+extern "C" int fcvm_comm_allreduce_max(fcvm_ctx *c, double *dev, int64_t n);
 
 namespace {
 
@@ -335,6 +336,15 @@ int deflation_build(fcvm_ctx *c) {
     int herr = 0;
     FCVM_CUDA(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
     FCVM_CUDA(cudaStreamSynchronize(st));
+    if (c->world > 1) {
+      // every rank must take the same exit (collectives follow): the worst flag of all ranks decides
+      double flag = (double)herr;
+      FCVM_CUDA(cudaMemcpyAsync(c->d_rhs, &flag, sizeof(double), cudaMemcpyHostToDevice, st));
+      FCVM_TRY(fcvm_comm_allreduce_max(c, c->d_rhs, 1));
+      FCVM_CUDA(cudaMemcpyAsync(&flag, c->d_rhs, sizeof(double), cudaMemcpyDeviceToHost, st));
+      FCVM_CUDA(cudaStreamSynchronize(st));
+      herr = (int)flag;
+    }
     FCVM_CHECK(herr == 0, FCVM_E_ARG,
                "deflation: a node couples to %s -- the clusters must be at least two elements wide in every direction",
                herr == 1 ? "a cluster that is not a neighbour of its own" : "more than eight clusters");
