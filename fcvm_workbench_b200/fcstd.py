@@ -159,11 +159,57 @@ class _BoxShape:
         return np.nonzero(np.abs(coords[:, axis] - val) <= tol)[0]
 
 
+class _SampledPlanarFaces:
+    """Faces of an arbitrary solid, as far as a constraint needs them: FreeCAD stores with every constraint a
+    sample of points (and normals) on the faces it references (properties ``Points`` / ``Normals``).  For planar
+    faces that is enough to find the mesh nodes on them without a CAD kernel: the samples are grouped by plane,
+    and the nodes of a face are the mesh nodes in that plane within the bounding box of its samples (the samples
+    include the face boundary; the body meets the plane only in the face)."""
+
+    def __init__(self, points: np.ndarray, normals: np.ndarray):
+        self.planes = []
+        n = normals / np.maximum(np.linalg.norm(normals, axis=1, keepdims=True), 1e-300)
+        d = np.einsum("ij,ij->i", points, n)
+        scale = max(float(np.abs(points).max()), 1.0)
+        key = np.round(np.c_[n, d / scale], 6)
+        for k in np.unique(key, axis=0):
+            sel = np.all(key == k, axis=1)
+            pts = points[sel]
+            # a planar face contributes a whole grid of samples with one normal; a curved face scatters its
+            # samples over as many (normal, offset) pairs as it has points
+            if len(pts) < 3 or np.linalg.matrix_rank(pts - pts[0], tol=1e-9 * scale) > 2:
+                raise NotImplementedError("constraint on a curved face: only planar faces are resolved headlessly")
+            self.planes.append((n[sel][0], float(d[sel].mean()), pts.min(axis=0), pts.max(axis=0)))
+
+    def nodes(self, coords: np.ndarray, tol: float) -> np.ndarray:
+        on = np.zeros(len(coords), dtype=bool)
+        for nrm, d, lo, hi in self.planes:
+            on |= (np.abs(coords @ nrm - d) <= tol) & np.all((coords >= lo - tol) & (coords <= hi + tol), axis=1)
+        return np.nonzero(on)[0]
+
+
+def _vector_list(z, obj, name):
+    """A ``PropertyVectorList`` stored as a separate binary file of the archive (uint32 count, 3 doubles each)."""
+    p = _prop(obj, name)
+    node = p.find("VectorList") if p is not None else None
+    if node is None or not node.get("file"):
+        return None
+    raw = z.read(node.get("file"))
+    n = int(np.frombuffer(raw[:4], dtype="<u4")[0])
+    dt = "<f8" if len(raw) == 4 + 24 * n else "<f4"
+    return np.frombuffer(raw[4:], dtype=dt, count=3 * n).reshape(n, 3).astype(np.float64)
+
+
 def read_fcstd(path: str) -> Model:
     """Build the ``setUpInput`` arrays from a ``.FCStd`` archive."""
     with zipfile.ZipFile(path) as z:
         doc = ET.fromstring(z.read("Document.xml"))
         unv = z.read("FemMesh.unv").decode()
+        sampled = {}
+        for o in doc.find("ObjectData").findall("Object"):
+            pts, nrm = _vector_list(z, o, "Points"), _vector_list(z, o, "Normals")
+            if pts is not None and nrm is not None and len(pts) == len(nrm) and len(pts) > 0:
+                sampled[o.get("name")] = (pts, nrm)
     label = None
     props = doc.find("Properties")
     if props is not None:
@@ -232,7 +278,19 @@ def read_fcstd(path: str) -> Model:
                 free = [_bool(o, "xFree", True), _bool(o, "yFree", True), _bool(o, "zFree", True)]
                 vals = [_float(o, "xDisplacement"), _float(o, "yDisplacement"), _float(o, "zDisplacement")]
             bc = []
-            for obj_name, sub in _refs(o):
+            refs = _refs(o)
+            if refs and any(on not in shapes for on, _ in refs) and name in sampled:
+                # not a Part::Box: vertices are the stored points themselves, planar faces are recovered from
+                # the samples stored with the constraint
+                if all(sub.startswith("Vertex") for _, sub in refs):
+                    for pnt in sampled[name][0]:
+                        bc.extend((np.nonzero(np.linalg.norm(nocoord - pnt, axis=1) <= tol)[0] + 1).tolist())
+                elif all(sub.startswith("Face") for _, sub in refs):
+                    bc.extend((_SampledPlanarFaces(*sampled[name]).nodes(nocoord, tol) + 1).tolist())
+                else:
+                    raise NotImplementedError("mixed vertex / edge / face references on a shape that is not a Part::Box")
+                refs = []
+            for obj_name, sub in refs:
                 bc.extend((shape_of(obj_name).nodes_on(sub, nocoord, tol) + 1).tolist())
             bc = list(dict.fromkeys(bc))
             if bc:

@@ -19,6 +19,7 @@ Fixtures
 ``cube2_gnly``     large-displacement branch (calcTSM every iteration).
 ``vm_uniaxial_tension`` the reference's VM_Uniaxial_Tension_Example (BASELINE config 0) with its control file.
 ``simple_shear``   the reference's Simple Shear model with its control file.
+``embankment``     the reference's Embankment_with_Ditch_Example (BASELINE config 2) with its control file.
 ``cube2_elastic``  nstep = 1: the linear-elastic analysis (no load stepping).
 ``column_buckling`` GNLY with imperfection: linear buckling (eigsh), imperfect geometry, restart.
 ``kernels``        single calls of calcGSM (element matrices), update_stress_load
@@ -172,6 +173,7 @@ def main():
     elastic_case()
     uniaxial_case()
     simple_shear_case()
+    embankment_case()
     buckling_case()
     kernel_case()
 
@@ -190,6 +192,15 @@ def simple_shear_case():
     m = read_fcstd(os.path.join(rh.REFERENCE_ROOT, "freeCAD files", "Simple Shear.FCStd"))
     c = read_control(os.path.join(rh.REFERENCE_ROOT, "control files", "Simple Shear.inp"))
     analysis_case("simple_shear", m, c)
+
+
+def embankment_case():
+    """BASELINE config 2: the reference's Embankment_with_Ditch_Example (659 elements, gravity-driven collapse
+    of a soil body in plane strain) with its control file; reproduces the committed
+    ``output files/Embankment_with_Ditch_Example.out``."""
+    m = read_fcstd(os.path.join(rh.REFERENCE_ROOT, "freeCAD files", "Embankment_with_Ditch_Example.FCStd"))
+    c = read_control(os.path.join(rh.REFERENCE_ROOT, "control files", "Embankment_with_Ditch_Example.inp"))
+    analysis_case("embankment", m, c)
 
 
 def buckling_case():

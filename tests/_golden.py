@@ -7,7 +7,7 @@ from fcvm_workbench_b200.control import Control
 from fcvm_workbench_b200.model import Model
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ANALYSES = ("tensile", "vm_uniaxial_tension", "simple_shear", "cube2_platen", "cube2_force", "cube2_gnly", "cube2_elastic")
+ANALYSES = ("tensile", "vm_uniaxial_tension", "simple_shear", "embankment", "cube2_platen", "cube2_force", "cube2_gnly", "cube2_elastic")
 ORACLE_ONLY = ("column_buckling",)      # branches the oracle restates but the CUDA path does not cover yet
 
 

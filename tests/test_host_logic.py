@@ -172,3 +172,28 @@ def test_fcstd_reader_resolves_box_vertices_of_the_uniaxial_example():
     box = _BoxShape(10.0, 10.0, 10.0)
     assert list(box.vertex("Vertex2")) == [0, 0, 0] and list(box.vertex("Vertex4")) == [0, 10, 0]
     assert list(box.vertex("Vertex6")) == [10, 0, 0] and list(box.vertex("Vertex1")) == [0, 0, 10]
+
+
+def test_fcstd_reader_resolves_planar_faces_from_stored_samples():
+    """BASELINE config 2: constraints on faces of a Part::Extrusion, found through the points / normals FreeCAD
+    stores with each constraint."""
+    path = "/root/reference/freeCAD files/Embankment_with_Ditch_Example.FCStd"
+    if not os.path.isfile(path):
+        pytest.skip("reference models not present on this machine")
+    from fcvm_workbench_b200.fcstd import read_fcstd, _SampledPlanarFaces
+    m = read_fcstd(path)
+    assert (m.ne, m.nn) == (659, 1418)
+    xyz = m.nocoord
+    mask = np.zeros(3 * m.nn, bool)
+    mask[list(m.fix)] = True
+    mask = mask.reshape(-1, 3)
+    clamped = (np.abs(xyz[:, 0]) < 1e-6) | (np.abs(xyz[:, 0] - 16000) < 1e-6) | (np.abs(xyz[:, 2]) < 1e-6)
+    ends = (np.abs(xyz[:, 1]) < 1e-6) | (np.abs(xyz[:, 1] + 1000) < 1e-6)
+    assert mask[clamped].all()                                   # fixed faces: all three dofs
+    assert mask[ends & ~clamped][:, 1].all() and not mask[ends & ~clamped][:, [0, 2]].any()   # plane strain: uy only
+    assert not mask[~clamped & ~ends].any()
+    # curved faces are refused, not guessed
+    t = np.linspace(0, np.pi / 2, 7)
+    pts = np.c_[np.cos(t), np.sin(t), 0 * t]
+    with pytest.raises(NotImplementedError):
+        _SampledPlanarFaces(np.vstack([pts, pts + [0, 0, 1]]), np.vstack([pts, pts]))

@@ -75,3 +75,26 @@ def test_reader_opens_the_references_own_vtk_and_names_match(tmp_path):
     assert set(f) == set(mine)                                                                  # same point-data arrays
     # the committed file predates the node-order swap of setUpInput (fcVM.py:338-341): same elements, as sets
     assert np.array_equal(np.sort(conn, axis=1), np.sort(m.elNodes - 1, axis=1))
+
+
+def test_embankment_out_file_reproduces_the_committed_one(tmp_path):
+    """BASELINE config 2: the rows of the reference's committed Embankment_with_Ditch_Example.out, from the
+    golden fixture of that model.  The Gauss-point number (first column) may differ where two mirror-image
+    points of the plane-strain body tie for max(csr); every other character must match."""
+    ref_out = "/root/reference/output files/Embankment_with_Ditch_Example.out"
+    z = load("embankment")
+    m, c = model_of(z), control_of(z)
+    res = {k: z["r_" + k] for k in ("crip", "lout", "un", "peeqplot", "pplot", "svmplot", "triaxplot", "ecrplot", "csrplot")}
+    p = tmp_path / "e.out"
+    results.write_out(p, "Embankment_with_Ditch_Example", m.ne, m.nn, c.gnl, c.nstep, tuple(z["r_loadsum"]), res,
+                      x=gauss_point_coordinates(m.elNodes, m.nocoord))
+    mine = open(p).read().splitlines()
+    assert mine[1].split()[-1] == "659" and mine[2].split()[-1] == "1418"
+    rows = [ln for ln in mine[14:] if ln and ln[0] == " " and ln.strip()[0].isdigit()]
+    assert len(rows) == 31
+    if os.path.isfile(ref_out):
+        ref = open(ref_out).read().splitlines()
+        assert mine[:14] == ref[:14]
+        ref_rows = [ln for ln in ref[14:] if ln and ln[0] == " " and ln.strip()[0].isdigit()]
+        assert len(ref_rows) == len(rows)
+        assert [r[11:] for r in rows] == [r[11:] for r in ref_rows]
