@@ -701,8 +701,10 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
                         elif not mrr:
                             dl = dl0 / scale_re / restart
                             eng.axpby(dl / scale_re / restart, ue, 0.0, du)
+                        # unconditional in the reference (fcVM.py:1474): after MAXIMUM RESTARTS the last kept load
+                        # level is overwritten with lbd[step] + the last Riks dl
+                        lbd[step + 1] = lbd[step] + dl
                         if not mrr:
-                            lbd[step + 1] = lbd[step] + dl
                             stress_update()
                             # r = fixdof*(lbd*(glv+modf) - qin): fixdof*modf is modf on free dofs
                             eng.axpbypcz(1.0, glv, 1.0, modf, 0.0, f)

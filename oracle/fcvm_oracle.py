@@ -466,8 +466,8 @@ def calcDisp(model, ctl, clicks=(), factorize: Optional[Callable] = None, log: O
                     elif not mrr:
                         dl = dl0 / scale_re / restart
                         du = dl * ue / scale_re / restart
+                    lbd[step + 1] = lbd[step] + dl                             # unconditional, fcVM.py:1474
                     if not mrr:
-                        lbd[step + 1] = lbd[step] + dl
                         qin = np.zeros(ndof)
                         update_stress_load(gp10, elNodes, nocoord, mat, sig_yield, disp_new, du, sig_old, sig_new,
                                            sig_test, qin, Et_E, LD, pgp)

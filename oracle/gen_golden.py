@@ -20,6 +20,8 @@ Fixtures
 ``vm_uniaxial_tension`` the reference's VM_Uniaxial_Tension_Example (BASELINE config 0) with its control file.
 ``simple_shear``   the reference's Simple Shear model with its control file.
 ``embankment``     the reference's Embankment_with_Ditch_Example (BASELINE config 2) with its control file.
+``cube2_maxrestarts`` force + gravity past the limit load with a small ``iterat_max``: the analysis ends with
+                   MAXIMUM RESTARTS REACHED (fcVM.py:1460-1474: the last kept load level is overwritten).
 ``cube2_elastic``  nstep = 1: the linear-elastic analysis (no load stepping).
 ``column_buckling`` GNLY with imperfection: linear buckling (eigsh), imperfect geometry, restart.
 ``kernels``        single calls of calcGSM (element matrices), update_stress_load
@@ -170,6 +172,7 @@ def main():
                   clicks=["add"])
     analysis_case("cube2_gnly", cube_model(2, mode="platen", top_disp=0.4),
                   Control(sig_yield=240.0, nstep=6, error_max=1e-6, target_LF=2.0, Et_E=0.02, gnl="GNLY"))
+    max_restarts_case()
     elastic_case()
     uniaxial_case()
     simple_shear_case()
@@ -211,6 +214,15 @@ def buckling_case():
     c = Control(sig_yield=240.0, nstep=4, error_max=1e-6, target_LF=1.0, Et_E=0.02, gnl="GNLY", maxImp="0.05",
                 ev1="1.0", ev2="0.0")
     analysis_case("column_buckling", m, c, extra=("eigenval",))
+
+
+def max_restarts_case():
+    """The normal end of a collapse run: a step that does not converge within ``iterat_max`` after four
+    restarts (fcVM.py:1457-1474).  The reference drops the failed load level, then overwrites the last kept
+    one with ``lbd[step] + dl`` of the last Riks correction."""
+    analysis_case("cube2_maxrestarts", cube_model(2, mode="force", top_disp=300.0),
+                  Control(sig_yield=240.0, nstep=14, iterat_max=3, error_max=1e-8, target_LF=2.0, Et_E=0.0,
+                          grav_z=-3.0e6))
 
 
 def elastic_case():

@@ -7,7 +7,7 @@ from fcvm_workbench_b200.control import Control
 from fcvm_workbench_b200.model import Model
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ANALYSES = ("tensile", "vm_uniaxial_tension", "simple_shear", "embankment", "cube2_platen", "cube2_force", "cube2_gnly", "cube2_elastic")
+ANALYSES = ("tensile", "vm_uniaxial_tension", "simple_shear", "embankment", "cube2_platen", "cube2_force", "cube2_gnly", "cube2_elastic", "cube2_maxrestarts")
 ORACLE_ONLY = ("column_buckling",)      # branches the oracle restates but the CUDA path does not cover yet
 
 
@@ -67,3 +67,21 @@ def rel_plot(k, got, z, sel=slice(None)):
     elif k == "triaxplot":
         scale = max(scale, 1.0)
     return float(np.abs(a - b).max(initial=0.0) / max(scale, 1e-300))
+
+
+def logged_iters(messages):
+    """Newton iterations per load step as the reference prints them ("Step: n" / "Iteration: k, Error: e",
+    fcVM.py:1315, 1344, 1455) -- the same reading ``oracle/ref_harness.iterations_per_step`` applied when the
+    fixtures were written: a restart that converges at once leaves the count of the failed attempt, and a step
+    abandoned after MAXIMUM RESTARTS still shows up."""
+    its, cur = [], None
+    for msg in messages:
+        if msg.startswith("Step:") and "Load level" not in msg:
+            if cur is not None:
+                its.append(cur)
+            cur = 0
+        elif msg.startswith("Iteration:"):
+            cur = int(msg.split(",")[0].split(":")[1])
+    if cur is not None:
+        its.append(cur)
+    return its
