@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--n", type=int, default=55, help="cells per cube edge (elements = 6 n^3)")
     ap.add_argument("--rtol", type=float, default=1e-8, help="PCG relative residual per linear solve")
-    ap.add_argument("--cpu-n", type=int, default=12, help="cube edge of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=16, help="cube edge of the bounded CPU sample")
     ap.add_argument("--deflation", type=int, default=DEFLATION,
                     help="unknowns of the rigid-body-mode coarse level of the PCG preconditioner (0 = block-Jacobi only)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -167,6 +167,7 @@ class Sweep:
             self._sync()
             if self.stride:
                 dev.profile(self.stride)
+            dev.pcg_phase_times(reset=True)
             self.bytes0 = (getattr(self.eng, "h2d_bytes", 0), getattr(self.eng, "d2h_bytes", 0))
             self.launch0 = dev.launch_count()
             self.t0 = time.time()
@@ -178,6 +179,7 @@ class Sweep:
             self.ms = dev.timer_stop_ms()
             self.t1 = time.time()
             self.launch1 = dev.launch_count()
+            self.phases = dev.pcg_phase_times()
             self.bytes1 = (getattr(self.eng, "h2d_bytes", 0), getattr(self.eng, "d2h_bytes", 0))
             if self.stride:
                 self.prof = dev.profile_get()
@@ -231,29 +233,52 @@ def kernel_report(eng, model, prof, hbm_peak, world=1):
 
 
 def cpu_baseline(W, K, n):
-    """The oracle (CPU port of the reference routines + a direct sparse solve standing in for CHOLMOD)
-    on a bounded sample of the same workload, timed on this box's host cores."""
-    from oracle import fcvm_oracle as orc
+    """The reference's CPU path on a bounded sample of the same workload, timed on this box's host cores.
+
+    kind "reference": the UNMODIFIED reference (``oracle/_ref``, put there by ``oracle/make_ref.py`` at build time,
+    or /root/reference) -- its numba-jitted ``calcGSM`` / ``update_stress_load`` / ``update_PEEQ_CSR`` and its own
+    ``calcDisp`` driven through ``oracle/ref_harness.py``; scikit-sparse (CHOLMOD) is not installable offline, so
+    its ``cholesky`` / ``factor(b)`` are served by SuperLU (scipy) on the same matrix.  kind "port": the oracle
+    (C restatement of the numba routines + the same SuperLU solve), used when numba or the copy is missing."""
     m, c = workload(n)
-    stamps = []
-
-    def hook(d):
-        stamps.append(time.perf_counter())
-        if d["iterat_tot"] == W + K:
-            raise orc.StopAnalysis()
-
-    t_setup = time.perf_counter()
+    threads = os.environ.get("NUMBA_NUM_THREADS")
     try:
-        orc.calcDisp(m, c, on_iteration=hook)
-    except orc.StopAnalysis:
-        pass
-    if len(stamps) < W + K:
-        raise SystemExit("cpu sample ended before warmup+steps Newton iterations")
-    dt = stamps[W + K - 1] - stamps[W - 1]
-    return {"value": 4 * m.ne * K / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"cube n={n}: {m.ne} elements, {K} Newton iterations after {W} warm-up; modified Newton with "
-                      f"one SuperLU factorisation (CHOLMOD stand-in, {stamps[0] - t_setup:.1f} s, untimed) and "
-                      f"the C restatement of the numba element routines",
+        from oracle import ref_harness as rh
+        have_ref = rh.available()
+    except Exception:
+        have_ref = False
+    if have_ref:
+        import numba
+        dt, setup = rh.time_reference(m, c, W, K)
+        kind = "reference"
+        what = (f"the unmodified reference (numba {numba.__version__}, its jitted element routines are serial: "
+                f"NUMBA_NUM_THREADS={threads or numba.config.NUMBA_NUM_THREADS} has no effect) + its calcDisp; "
+                f"CHOLMOD stand-in: one SuperLU factorisation")
+    else:
+        from oracle import fcvm_oracle as orc
+        stamps = []
+
+        def hook(d):
+            stamps.append(time.perf_counter())
+            if d["iterat_tot"] == W + K:
+                raise orc.StopAnalysis()
+
+        t_setup = time.perf_counter()
+        try:
+            orc.calcDisp(m, c, on_iteration=hook)
+        except orc.StopAnalysis:
+            pass
+        if len(stamps) < W + K:
+            raise SystemExit("cpu sample ended before warmup+steps Newton iterations")
+        dt, setup = stamps[W + K - 1] - stamps[W - 1], stamps[0] - t_setup
+        kind = "port"
+        what = "the oracle port (C restatement of the numba element routines) + one SuperLU factorisation"
+    return {"value": 4 * m.ne * K / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "numba_num_threads": threads,
+            "host_cores": os.cpu_count(),
+            "sample": f"cube n={n}: {m.ne} elements, {K} Newton iterations after {W} warm-up of the same platen sweep; "
+                      f"{what} (set-up incl. factorisation {setup:.1f} s, untimed); a direct factorisation of the "
+                      f"full n=55 system (4.1M dofs) does not fit the time box",
             "newton_iters_per_s": K / dt, "ms_per_step": 1e3 * dt / K, "elements": m.ne}
 
 
@@ -391,6 +416,8 @@ def main():
                          "algorithmic_bytes_per_launch": spmv.get("algorithmic_bytes"),
                          "avg_launch_ms": spmv.get("avg_ms_per_product", spmv.get("avg_ms"))},
             "kernels": kern,
+            "pcg_phases_ms_per_iteration": ({k: round(v / max(sw.phases[1], 1), 5) for k, v in sw.phases[0].items()}
+                                            if sw.phases[1] else None),
             "cpu_baseline": cb,
             "clocks": clk,
             "setup_s": {"mesh": round(t_mesh, 2)},

@@ -11,7 +11,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int16, c_int64, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfcvm_b200.so")
+LIB_PATH = os.environ.get("FCVM_LIB_PATH") or os.path.join(_HERE, "libfcvm_b200.so")   # override: kernel experiments
 
 f64p = POINTER(c_double)
 i64p = POINTER(c_int64)
@@ -27,6 +27,7 @@ class FcvmError(RuntimeError):
 
 
 E_NOCONV = -4
+E_INDEFINITE = -6
 
 # name -> (argtypes); every function returns int unless listed in _RESTYPE
 _SIGNATURES = {
@@ -61,6 +62,7 @@ _SIGNATURES = {
     "fcvm_spmv": [ctxp, c_void_p, c_void_p],
     "fcvm_set_deflation": [ctxp, c_int, c_int, c_int, POINTER(ctypes.c_int32), f64p, f64p, u8p],
     "fcvm_pcg_solve": [ctxp, c_void_p, c_void_p, c_double, c_int, c_int, POINTER(c_int), f64p],
+    "fcvm_pcg_phase_times": [ctxp, f64p, i64p, c_int],
     "fcvm_update_stress_load": [ctxp, c_void_p, c_void_p, c_void_p, c_double, c_int, c_double],
     "fcvm_update_peeq_csr": [ctxp, c_double, c_double, i64p, f64p],
     "fcvm_scale_step_stress": [ctxp, c_double],

@@ -160,6 +160,20 @@ struct fcvm_ctx {
   double *dE = nullptr, *dEinv = nullptr;             // [6 ncl][6 ncl]
   double *d_rhs = nullptr, *d_lam = nullptr;          // [6 ncl]
   double *spmv_part2 = nullptr; // per-slice partials of r.u
+  // fused (persistent, cooperative) PCG kernel: chunked coarse work lists, single-precision copies of the
+  // coarse operators (they only shape the preconditioner), slice ranges of the SpMV workers
+  int32_t *it_box = nullptr, *it_lo = nullptr, *it_hi = nullptr, *box_item_ptr = nullptr;
+  uint8_t *it_kind = nullptr;
+  int64_t n_items = 0;
+  double *item_part = nullptr;  // [n_items][6]
+  float *kz32 = nullptr;        // [18][nent]
+  float *einv32 = nullptr;      // [6 ncl][6 ncl]
+  double *lam4 = nullptr;       // [4][6 ncl] column-quarter partials of E^-1 rhs
+  int32_t *wk_slice = nullptr;  // [workers + 1] slice range of every SpMV worker
+  int wk_grid = 0, wk_split = 0;
+  double *fused_part = nullptr; // [4][grid] block partials of the in-kernel dot products
+  unsigned long long *phase_ns = nullptr;   // [8] device time per phase of the fused kernel, [8] = iterations
+  int fused_grid = 0;           // co-resident blocks of the fused kernel (0 = not yet queried)
   void *cusolver = nullptr;
   double *cus_work = nullptr;
   int cus_lwork = 0;
@@ -212,64 +226,8 @@ struct ProfScope {
 };
 
 // ---------------------------------------------------------------------------------------
-// Device helpers: 10-node tetrahedron at Gauss point GP (0..3).
-// Local derivative table of fcVM.py:390-424 with the Gauss coordinates folded in at
-// compile time; zero entries vanish from the generated code.
-// ---------------------------------------------------------------------------------------
-template <int GP>
-struct GaussPt {
-  static constexpr double xi = (GP == 1) ? GP_B : GP_A;
-  static constexpr double et = (GP == 2) ? GP_B : GP_A;
-  static constexpr double ze = (GP == 3) ? GP_B : GP_A;
-  static constexpr double a4 = 1.0 - 4.0 * (1.0 - xi - et - ze);
-};
-
-// sum_k v[k][i] * dN[j][k]  for j = 0,1,2  (v: 10 nodal 3-vectors)  -> out[i][j]
-template <int GP>
-__device__ __forceinline__ void local_gradient(const double (&v)[10][3], double (&out)[3][3]) {
-  constexpr double xi = GaussPt<GP>::xi, et = GaussPt<GP>::et, ze = GaussPt<GP>::ze, a4 = GaussPt<GP>::a4;
-  constexpr double d01 = 4.0 * xi - 1.0, d04 = 4.0 * (1.0 - 2.0 * xi - et - ze);
-  constexpr double d12 = 4.0 * et - 1.0, d16 = 4.0 * (1.0 - xi - 2.0 * et - ze);
-  constexpr double d23 = 4.0 * ze - 1.0, d27 = 4.0 * (1.0 - xi - et - 2.0 * ze);
-  constexpr double x4 = 4.0 * xi, e4 = 4.0 * et, z4 = 4.0 * ze;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    // xi-derivative: nodes 0,1,4,5,6,7,8
-    out[i][0] = a4 * v[0][i] + d01 * v[1][i] + d04 * v[4][i] + e4 * (v[5][i] - v[6][i]) + z4 * (v[8][i] - v[7][i]);
-    // eta-derivative: nodes 0,2,4,5,6,7,9
-    out[i][1] = a4 * v[0][i] + d12 * v[2][i] + x4 * (v[5][i] - v[4][i]) + d16 * v[6][i] + z4 * (v[9][i] - v[7][i]);
-    // zeta-derivative: nodes 0,3,4,6,7,8,9
-    out[i][2] = a4 * v[0][i] + d23 * v[3][i] - x4 * v[4][i] - e4 * v[6][i] + d27 * v[7][i] + x4 * v[8][i] +
-                e4 * v[9][i];
-  }
-}
-
-// F[k][i] += sum_j T[i][j] * dN[j][k]  (transpose of local_gradient, same constants)
-template <int GP>
-__device__ __forceinline__ void scatter_gradient(const double (&T)[3][3], double (&F)[10][3]) {
-  constexpr double xi = GaussPt<GP>::xi, et = GaussPt<GP>::et, ze = GaussPt<GP>::ze, a4 = GaussPt<GP>::a4;
-  constexpr double d01 = 4.0 * xi - 1.0, d04 = 4.0 * (1.0 - 2.0 * xi - et - ze);
-  constexpr double d12 = 4.0 * et - 1.0, d16 = 4.0 * (1.0 - xi - 2.0 * et - ze);
-  constexpr double d23 = 4.0 * ze - 1.0, d27 = 4.0 * (1.0 - xi - et - 2.0 * ze);
-  constexpr double x4 = 4.0 * xi, e4 = 4.0 * et, z4 = 4.0 * ze;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    const double t0 = T[i][0], t1 = T[i][1], t2 = T[i][2];
-    F[0][i] += a4 * (t0 + t1 + t2);
-    F[1][i] += d01 * t0;
-    F[2][i] += d12 * t1;
-    F[3][i] += d23 * t2;
-    F[4][i] += d04 * t0 - x4 * (t1 + t2);
-    F[5][i] += e4 * t0 + x4 * t1;
-    F[6][i] += d16 * t1 - e4 * (t0 + t2);
-    F[7][i] += d27 * t2 - z4 * (t0 + t1);
-    F[8][i] += z4 * t0 + x4 * t2;
-    F[9][i] += z4 * t1 + e4 * t2;
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// Run-time Gauss point: the non-zero entries of the derivative table are ten numbers that depend
+// 10-node tetrahedron, run-time Gauss point (local derivative table of fcVM.py:390-424): the non-zero
+// entries of the derivative table are ten numbers that depend
 // on the point only through (xi, eta, zeta).  One code path for all four points keeps the kernel
 // small enough for the instruction cache (four compile-time copies of the stress update did not).
 // ---------------------------------------------------------------------------------------
@@ -375,74 +333,6 @@ __device__ __forceinline__ double invert_jacobian(const double (&xs)[3][3], doub
   xsi[2][1] = (xs[2][0] * xs[0][1] - xs[0][0] * xs[2][1]) * inv;
   xsi[2][2] = (xs[0][0] * xs[1][1] - xs[1][0] * xs[0][1]) * inv;
   return xsj;
-}
-
-// dN[j][k] as a compile-time constant
-template <int GP>
-__device__ __forceinline__ constexpr double dN(int j, int k) {
-  constexpr double xi = GaussPt<GP>::xi, et = GaussPt<GP>::et, ze = GaussPt<GP>::ze, a4 = GaussPt<GP>::a4;
-  if (j == 0) {
-    switch (k) {
-      case 0: return a4;
-      case 1: return 4.0 * xi - 1.0;
-      case 4: return 4.0 * (1.0 - 2.0 * xi - et - ze);
-      case 5: return 4.0 * et;
-      case 6: return -4.0 * et;
-      case 7: return -4.0 * ze;
-      case 8: return 4.0 * ze;
-      default: return 0.0;
-    }
-  } else if (j == 1) {
-    switch (k) {
-      case 0: return a4;
-      case 2: return 4.0 * et - 1.0;
-      case 4: return -4.0 * xi;
-      case 5: return 4.0 * xi;
-      case 6: return 4.0 * (1.0 - xi - 2.0 * et - ze);
-      case 7: return -4.0 * ze;
-      case 9: return 4.0 * ze;
-      default: return 0.0;
-    }
-  } else {
-    switch (k) {
-      case 0: return a4;
-      case 3: return 4.0 * ze - 1.0;
-      case 4: return -4.0 * xi;
-      case 6: return -4.0 * et;
-      case 7: return 4.0 * (1.0 - xi - et - 2.0 * ze);
-      case 8: return 4.0 * xi;
-      case 9: return 4.0 * et;
-      default: return 0.0;
-    }
-  }
-}
-
-// shape functions N_k at Gauss point GP (fcVM.py:364-380)
-template <int GP>
-__device__ __forceinline__ constexpr double shpN(int k) {
-  constexpr double xi = GaussPt<GP>::xi, et = GaussPt<GP>::et, ze = GaussPt<GP>::ze;
-  constexpr double a = 1.0 - xi - et - ze;
-  switch (k) {
-    case 0: return (2.0 * a - 1.0) * a;
-    case 1: return xi * (2.0 * xi - 1.0);
-    case 2: return et * (2.0 * et - 1.0);
-    case 3: return ze * (2.0 * ze - 1.0);
-    case 4: return 4.0 * xi * a;
-    case 5: return 4.0 * xi * et;
-    case 6: return 4.0 * et * a;
-    case 7: return 4.0 * ze * a;
-    case 8: return 4.0 * xi * ze;
-    default: return 4.0 * et * ze;
-  }
-}
-
-// Jacobian xs[i][j] = d x_i / d xi_j, its determinant and inverse xsi (fcVM.py:428-453):
-// dshpg[m][k] = sum_j xsi[j][m] * dN[j][k]
-template <int GP>
-__device__ __forceinline__ double jacobian(const double (&X)[10][3], double (&xsi)[3][3]) {
-  double xs[3][3];
-  local_gradient<GP>(X, xs);
-  return invert_jacobian(xs, xsi);
 }
 
 // block-level deterministic sum: fixed tree over the warp, then over warps in order

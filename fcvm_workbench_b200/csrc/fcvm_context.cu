@@ -308,10 +308,12 @@ extern "C" int fcvm_create(fcvm_ctx **out, int device) {
 
 namespace fcvm {
 void deflation_free(fcvm_ctx *c);
+void fused_free_mesh(fcvm_ctx *c);
 }
 
 static void free_mesh(fcvm_ctx *c) {
   deflation_free(c);
+  fused_free_mesh(c);
   dfree(c->conn); dfree(c->xyz); dfree(c->n2e_ptr); dfree(c->n2e_idx); dfree(c->elv);
   dfree(c->fixmask); dfree(c->fixval); dfree(c->movmask);
   for (int i = 0; i < FCVM_BUF_COUNT; i++) {
@@ -344,6 +346,7 @@ extern "C" int fcvm_destroy(fcvm_ctx *c) {
   if (c->cusolver) cusolverDnDestroy((cusolverDnHandle_t)c->cusolver);
   if (c->cus_work) cudaFree(c->cus_work);
   if (c->cus_info) cudaFree(c->cus_info);
+  if (c->phase_ns) cudaFree(c->phase_ns);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);

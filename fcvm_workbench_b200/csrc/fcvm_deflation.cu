@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "fcvm_common.cuh"
+#include "fcvm_deflation.cuh"
 #include "fcvm_reduce.cuh"
 
 using namespace fcvm;
@@ -23,41 +24,6 @@ extern "C" int fcvm_comm_allreduce_sum(fcvm_ctx *c, double *dev, int64_t n);
 extern "C" int fcvm_comm_allreduce_max(fcvm_ctx *c, double *dev, int64_t n);
 
 namespace {
-
-struct Grid {
-  int n[3];
-  double lo[3], h[3], scale;
-  const uint8_t *active;     // per box: 0 = too few free nodes for six independent modes, its columns of Z are zero
-};
-
-// Z_j: 3 x 6 = [ I | (e_k x rel)/scale ], rows of prescribed dofs zeroed
-__device__ __forceinline__ void z_of(const Grid &g, int32_t cl, const double *__restrict__ xyz, const double *__restrict__ fixdof,
-                                     int64_t j, double (&Z)[3][6]) {
-  const int ix = cl % g.n[0], iy = (cl / g.n[0]) % g.n[1], iz = cl / (g.n[0] * g.n[1]);
-  const double rx = (xyz[3 * j] - (g.lo[0] + (ix + 0.5) * g.h[0])) / g.scale;
-  const double ry = (xyz[3 * j + 1] - (g.lo[1] + (iy + 0.5) * g.h[1])) / g.scale;
-  const double rz = (xyz[3 * j + 2] - (g.lo[2] + (iz + 0.5) * g.h[2])) / g.scale;
-  const double on = g.active[cl] ? 1.0 : 0.0;
-  const double f0 = on * fixdof[3 * j], f1 = on * fixdof[3 * j + 1], f2 = on * fixdof[3 * j + 2];
-  // e_x x r = (0, -rz, ry), e_y x r = (rz, 0, -rx), e_z x r = (-ry, rx, 0)
-  Z[0][0] = f0; Z[0][1] = 0;  Z[0][2] = 0;  Z[0][3] = 0;        Z[0][4] = f0 * rz;  Z[0][5] = -f0 * ry;
-  Z[1][0] = 0;  Z[1][1] = f1; Z[1][2] = 0;  Z[1][3] = -f1 * rz; Z[1][4] = 0;        Z[1][5] = f1 * rx;
-  Z[2][0] = 0;  Z[2][1] = 0;  Z[2][2] = f2; Z[2][3] = f2 * ry;  Z[2][4] = -f2 * rx; Z[2][5] = 0;
-}
-
-__device__ __forceinline__ int rel_code(const Grid &g, int32_t from, int32_t to) {
-  const int nx = g.n[0], ny = g.n[1];
-  const int dx = to % nx - from % nx, dy = (to / nx) % ny - (from / nx) % ny, dz = to / (nx * ny) - from / (nx * ny);
-  if (dx < -1 || dx > 1 || dy < -1 || dy > 1 || dz < -1 || dz > 1) return -1;
-  return (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1);
-}
-
-__device__ __forceinline__ int32_t neighbour(const Grid &g, int32_t cl, int code) {
-  const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
-  const int ix = cl % nx + code % 3 - 1, iy = (cl / nx) % ny + (code / 3) % 3 - 1, iz = cl / (nx * ny) + code / 9 - 1;
-  if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) return -1;
-  return ix + nx * (iy + ny * iz);
-}
 
 // (K Z)_(i, c') for every block row i: one thread per row, walking its SELL slice.  Slot t of a row is
 // the t-th distinct box met along the row (purely structural).  Structure pass (ent_inv == nullptr):
@@ -253,18 +219,6 @@ __global__ void k_expand(int64_t nn, Grid g, const int32_t *__restrict__ cid, co
   }
 }
 
-Grid grid_of(const fcvm_ctx *c) {
-  Grid g;
-  for (int d = 0; d < 3; d++) {
-    g.n[d] = c->dn[d];
-    g.lo[d] = c->dlo[d];
-    g.h[d] = c->dh[d];
-  }
-  g.scale = c->dscale;
-  g.active = c->cl_active;
-  return g;
-}
-
 template <typename T>
 int dalloc2(T **p, int64_t n) {
   if (*p) cudaFree(*p);
@@ -321,6 +275,10 @@ extern "C" int fcvm_set_deflation(fcvm_ctx *c, int ncx, int ncy, int ncz, const 
 
 namespace fcvm {
 
+int fused_build_items(fcvm_ctx *c, const std::vector<int32_t> &cl_ptr, const std::vector<int32_t> &ent_ptr);
+int fused_refresh_coarse(fcvm_ctx *c);
+void fused_free(fcvm_ctx *c);
+
 // K Z, E = Z^T K Z and its inverse for the matrix now in the context (called at the end of fcvm_assemble)
 int deflation_build(fcvm_ctx *c) {
   c->defl_ready = false;
@@ -329,8 +287,8 @@ int deflation_build(fcvm_ctx *c) {
   const Grid g = grid_of(c);
   const int64_t nn = c->nn, ncl = c->ncl, n6 = 6 * ncl;
   const double *fixdof = (const double *)c->buf[FCVM_BUF_FIXDOF];
-  int *derr;
-  FCVM_CUDA(cudaMalloc((void **)&derr, sizeof(int)));
+  if (!c->cus_info) FCVM_CUDA(cudaMalloc((void **)&c->cus_info, sizeof(int) * 2));
+  int *derr = c->cus_info + 1;                    // structure-error flag of the K Z kernels
   FCVM_CUDA(cudaMemsetAsync(derr, 0, sizeof(int), st));
   auto check = [&]() -> int {
     int herr = 0;
@@ -356,7 +314,7 @@ int deflation_build(fcvm_ctx *c) {
     k_build_kz<<<grid_for(c->nslices * SELL_C, 128), 128, 0, st>>>(c->nslices, g, c->slice_ptr, c->slot_node, c->colidx,
                                                                   c->vals, c->xyz, fixdof, c->d_cid, c->kz_rel, nullptr,
                                                                   nullptr, 0, derr);
-    if (int rc = check()) { cudaFree(derr); return rc; }
+    FCVM_TRY(check());
     std::vector<int8_t> rel((size_t)8 * nn);
     std::vector<int32_t> cid((size_t)nn);
     FCVM_CUDA(cudaMemcpy(rel.data(), c->kz_rel, (size_t)8 * nn, cudaMemcpyDeviceToHost));
@@ -383,13 +341,17 @@ int deflation_build(fcvm_ctx *c) {
     FCVM_CUDA(cudaMemcpy(c->ent_ptr, ptr.data(), sizeof(int32_t) * (ncl + 1), cudaMemcpyHostToDevice));
     FCVM_CUDA(cudaMemcpy(c->ent, ent_node.data(), sizeof(int32_t) * nent, cudaMemcpyHostToDevice));
     FCVM_CUDA(cudaMemcpy(c->ent_inv, inv.data(), sizeof(int32_t) * 8 * nn, cudaMemcpyHostToDevice));
+    std::vector<int32_t> clp((size_t)ncl + 1);
+    FCVM_CUDA(cudaMemcpy(clp.data(), c->cl_ptr, sizeof(int32_t) * (ncl + 1), cudaMemcpyDeviceToHost));
+    FCVM_TRY(fused_build_items(c, clp, ptr));
+    cudaFree(c->kz32); cudaFree(c->einv32);       // sized by nent / ncl: reallocated by the refresh below
+    c->kz32 = c->einv32 = nullptr;
     c->defl_structure = true;
   }
   k_build_kz<<<grid_for(c->nslices * SELL_C, 128), 128, 0, st>>>(c->nslices, g, c->slice_ptr, c->slot_node, c->colidx,
                                                                 c->vals, c->xyz, fixdof, c->d_cid, c->kz_rel, c->ent_inv,
                                                                 c->kz_val, c->nent, derr);
-  if (int rc = check()) { cudaFree(derr); return rc; }
-  cudaFree(derr);
+  FCVM_TRY(check());
   FCVM_CUDA(cudaMemsetAsync(c->dE, 0, sizeof(double) * n6 * n6, st));
   k_build_e<<<(unsigned)ncl, 288, 0, st>>>(g, ncl, c->cl_ptr, c->cl_nodes, c->kz_rel, c->ent_inv, c->kz_val, c->nent, c->xyz,
                                            fixdof, c->dE);
@@ -401,7 +363,6 @@ int deflation_build(fcvm_ctx *c) {
   if (!h) {
     FCVM_CHECK(cusolverDnCreate(&h) == CUSOLVER_STATUS_SUCCESS, FCVM_E_CUDA, "cusolverDnCreate failed");
     c->cusolver = (void *)h;
-    FCVM_CUDA(cudaMalloc((void **)&c->cus_info, sizeof(int)));
   }
   cusolverDnSetStream(h, st);
   int lw1 = 0, lw2 = 0;
@@ -424,6 +385,7 @@ int deflation_build(fcvm_ctx *c) {
   k_mirror<<<grid_for(n6 * n6, 256), 256, 0, st>>>(n6, c->dE, c->dEinv);
   FCVM_CUDA(cudaGetLastError());
   c->launches += 5;
+  FCVM_TRY(fused_refresh_coarse(c));
   c->defl_ready = true;
   return FCVM_OK;
 }
@@ -455,6 +417,7 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
 }
 
 void deflation_free(fcvm_ctx *c) {
+  fused_free(c);
   cudaFree(c->cl_active); c->cl_active = nullptr;
   cudaFree(c->d_cid); cudaFree(c->cl_ptr); cudaFree(c->cl_nodes); cudaFree(c->kz_rel); cudaFree(c->kz_val);
   cudaFree(c->ent_ptr); cudaFree(c->ent); cudaFree(c->ent_inv); c->ent_inv = nullptr; cudaFree(c->dE); cudaFree(c->dEinv); cudaFree(c->d_rhs); cudaFree(c->d_lam);

@@ -9,6 +9,7 @@
 // the rigid-body-mode deflation level of fcvm_deflation.cu when switched on.  On a partitioned mesh the
 // interface exchange of w overlaps the interior part of the product (communication stream).
 #include "fcvm_common.cuh"
+#include "fcvm_pcg.cuh"
 #include "fcvm_reduce.cuh"
 
 using namespace fcvm;
@@ -21,16 +22,6 @@ int fcvm_comm_allreduce_oop(fcvm_ctx *c, const double *send, double *recv, int64
 namespace {
 
 constexpr int CHECK_EVERY = 16;
-
-// Device scalar slots in ctx->red_out.  gamma = r.u, rr = r.r and alpha live in pairs indexed by
-// the parity of the iteration; L_* are per-rank partial sums on their way through the three-scalar
-// all-reduce when a communicator is attached.
-enum {
-  S_GAMMA = 0,   // [2]
-  S_RR = 2,      // [2]
-  S_ALPHA = 4,   // [2]
-  S_DELTA = 6, S_BB = 7, S_THR = 8, S_ITERS = 9, L_RU = 10, L_RR = 11, L_WU = 12, L_BB = 13
-};
 
 // y = K x on the block-SELL matrix.  One block per 32-row slice, SPMV_SPLIT warps per block: warp w
 // walks columns k0+w, k0+w+SPLIT, ... of the slice, so the column index and each of the nine block
@@ -183,6 +174,7 @@ k_pcg_init(int64_t nn, const double *__restrict__ b, const double *__restrict__ 
 __global__ void k_pcg_scalars(double rtol, double *sc) {
   sc[S_THR] = rtol * rtol * sc[S_BB];
   sc[S_ITERS] = -1.0;
+  sc[S_STATUS] = (double)PCG_RUNNING;
   sc[S_ALPHA] = sc[S_ALPHA + 1] = 0.0;
   sc[S_RR + 1] = sc[S_RR];              // both parity slots start from the initial residual
 }
@@ -202,15 +194,22 @@ k_pcg_step(int64_t nn, int it, int defl, const double *__restrict__ w, const dou
     return;
   }
   const double gam = sc[S_GAMMA + cur];
-  double beta = 0.0, alpha;
-  if (it == 0) {
-    alpha = sc[S_DELTA] != 0.0 ? gam / sc[S_DELTA] : 0.0;
-  } else {
+  double beta = 0.0, den = sc[S_DELTA];
+  if (it > 0) {
     const double gprev = sc[S_GAMMA + prv], aprev = sc[S_ALPHA + prv];
     beta = gprev != 0.0 ? gam / gprev : 0.0;
-    const double den = sc[S_DELTA] - (aprev != 0.0 ? beta * gam / aprev : 0.0);
-    alpha = den != 0.0 ? gam / den : 0.0;
+    den = sc[S_DELTA] - (aprev != 0.0 ? beta * gam / aprev : 0.0);
   }
+  if (!(gam > 0.0) || !(den > 0.0)) {
+    // operator or preconditioner not positive definite (a tangent at or past buckling, a floating model):
+    // stop here with a sticky flag instead of iterating on to the limit
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      sc[S_STATUS] = (double)PCG_BREAKDOWN;
+      sc[S_ITERS] = (double)it;
+    }
+    return;
+  }
+  const double alpha = gam / den;
   double v[2] = {0.0, 0.0};
   for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
     const int64_t d = 3 * n;
@@ -273,6 +272,8 @@ extern "C" int fcvm_spmv(fcvm_ctx *c, const double *x, double *y) {
 }
 
 namespace fcvm {
+bool pcg_fused_enabled(const fcvm_ctx *c);
+int pcg_fused_loop(fcvm_ctx *c, double *x, int max_iter);
 int interface_sum_on_comm_stream(fcvm_ctx *c, double *v);
 int comm_allreduce_on(fcvm_ctx *c, double *dev, int64_t n, cudaStream_t st);
 int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const double *base, double *out, const double *sc,
@@ -284,6 +285,8 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
   FCVM_CHECK(c && c->assembled && b && x, FCVM_E_ARG, "fcvm_pcg_solve: assemble first / null argument");
   FCVM_CHECK(rtol > 0.0 && max_iter > 0, FCVM_E_ARG, "fcvm_pcg_solve: rtol and max_iter must be positive");
   const int64_t nn = c->nn, n3 = 3 * nn;
+  // CG ends within ndof iterations in exact arithmetic; a small multiple of that is the most any caller can want
+  if ((int64_t)max_iter > 10 * n3 + 100) max_iter = (int)(10 * n3 + 100);
   cudaStream_t st = c->stream;
   double *sc = c->red_out;
   const double *w = c->dof_weight;
@@ -372,9 +375,23 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
     }
     return FCVM_OK;
   };
-  FCVM_TRY(spmv_dot(0));
   int it = 0, n_it = -1;
-  while (n_it < 0 && it < max_iter) {
+  const bool fused = pcg_fused_enabled(c);
+  if (fused) {
+    // the whole loop in one persistent cooperative kernel (fcvm_pcg_fused.cu)
+    ProfScope ps(c, 3);
+    FCVM_TRY(pcg_fused_loop(c, x, max_iter));
+  } else {
+    FCVM_TRY(spmv_dot(0));
+  }
+  if (fused) {
+    FCVM_CUDA(cudaGetLastError());
+    FCVM_CUDA(cudaMemcpyAsync(c->h_scalars, sc, sizeof(double) * 16, cudaMemcpyDeviceToHost, st));
+    FCVM_CUDA(cudaStreamSynchronize(st));
+    it = (int)c->h_scalars[S_ITERS];
+    if ((int)c->h_scalars[S_STATUS] == PCG_CONVERGED) n_it = it;
+  }
+  while (!fused && n_it < 0 && it < max_iter) {
     const int batch_end = std::min(max_iter, it + CHECK_EVERY);
     for (; it < batch_end; it++) {
       {
@@ -391,6 +408,10 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
     FCVM_CUDA(cudaGetLastError());
     FCVM_CUDA(cudaMemcpyAsync(c->h_scalars, sc, sizeof(double) * 16, cudaMemcpyDeviceToHost, st));
     FCVM_CUDA(cudaStreamSynchronize(st));
+    if ((int)c->h_scalars[S_STATUS] == PCG_BREAKDOWN) {
+      it = (int)c->h_scalars[S_ITERS];
+      break;
+    }
     if (c->h_scalars[S_ITERS] >= 0.0)
       n_it = (int)c->h_scalars[S_ITERS];
     else if (c->h_scalars[S_RR + (it & 1)] <= c->h_scalars[S_THR])
@@ -402,6 +423,12 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
   const double rr = c->h_scalars[S_RR + (n_it & 1)];
   if (iters) *iters = n_it;
   if (relres) *relres = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+  if (!conv && (int)c->h_scalars[S_STATUS] == PCG_BREAKDOWN) {
+    set_error("fcvm_pcg_solve: breakdown after %d iterations (p.Kp or r.M^-1 r not positive: the matrix is not positive "
+              "definite -- the reference's 'singular stiffness matrix', fcVM.py:1367-1381); relative residual %.3e",
+              n_it, bb > 0.0 ? sqrt(rr / bb) : 0.0);
+    return FCVM_E_INDEFINITE;
+  }
   if (!conv) {
     set_error("fcvm_pcg_solve: no convergence in %d iterations (relative residual %.3e, target %.3e)", max_iter,
               bb > 0.0 ? sqrt(rr / bb) : 0.0, rtol);

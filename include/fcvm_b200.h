@@ -40,9 +40,12 @@ enum {
   FCVM_OK = 0,
   FCVM_E_ARG = -1,     /* bad argument / call order */
   FCVM_E_CUDA = -2,    /* CUDA runtime error (no device, out of memory, launch failure) */
-  FCVM_E_MESH = -3,    /* inconsistent mesh (node number out of range, degenerate element) */
+  FCVM_E_MESH = -3,    /* inconsistent mesh (node number outside 1..nn).  An element with a non-positive Jacobian
+                          is NOT rejected: like the reference (fcVM.py:450, abs(xsj)) it is integrated with |J| */
   FCVM_E_NOCONV = -4,  /* PCG hit max_iter before reaching the tolerance */
-  FCVM_E_NCCL = -5     /* NCCL failure (multi-GPU) */
+  FCVM_E_NCCL = -5,    /* NCCL / peer-memory failure (multi-GPU) */
+  FCVM_E_INDEFINITE = -6 /* PCG breakdown: the matrix is not positive definite (the reference's 'singular stiffness
+                          matrix', fcVM.py:1367-1381) */
 };
 
 /* Named device buffers owned by the context (fcvm_buf). */
@@ -141,6 +144,11 @@ int fcvm_spmv(fcvm_ctx *ctx, const double *x, double *y);
  * recursively updated residual satisfies ||r|| <= rtol * ||b||; returns FCVM_E_NOCONV after max_iter. */
 int fcvm_pcg_solve(fcvm_ctx *ctx, const double *b, double *x, double rtol, int max_iter, int use_x0, int *iters,
                    double *relres);
+/* The iteration loop runs as ONE persistent cooperative kernel (phases separated by grid barriers, no host round
+ * trips).  Device time it spent per phase since the last reset, in ms: [0] vector step, [1] coarse partials
+ * (streams K Z), [2] coarse right-hand side, [3] coarse product (streams E^-1), [4] expansion u = y + Z lam,
+ * [5] product w = K u; *iterations = PCG iterations these cover. */
+int fcvm_pcg_phase_times(fcvm_ctx *ctx, double *ms6, int64_t *iterations, int reset);
 
 /* Second preconditioner level (optional): deflation of the rigid-body modes of box clusters of nodes.
  * The clusters form an ncx x ncy x ncz grid of boxes lo + (i,j,k)*h over the (global) bounding box;

@@ -34,7 +34,21 @@ import numpy as np
 import scipy.sparse as scsp
 import scipy.sparse.linalg as spla
 
-REFERENCE_ROOT = os.environ.get("FCVM_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    """Where the unmodified reference lies: $FCVM_REFERENCE_ROOT, /root/reference (the build container), or
+    ``oracle/_ref`` -- the git-ignored copy ``oracle/make_ref.py`` makes at build time so that the reference arm
+    of ``bench.py`` can run on the GPU box, where /root/reference does not exist."""
+    cands = [os.environ.get("FCVM_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "source code", "fcVM.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 _SRC = os.path.join(REFERENCE_ROOT, "source code", "fcVM.py")
 
 
@@ -197,3 +211,47 @@ def iterations_per_step(messages):
     if cur is not None:
         its.append(cur)
     return its
+
+
+class _StopTiming(Exception):
+    pass
+
+
+def time_reference(model, ctl, warmup: int, steps: int):
+    """Newton iterations ``warmup+1 .. warmup+steps`` of the reference's own ``calcGSM`` + ``calcDisp`` on
+    ``model`` / ``ctl``, timed from its progress lines ("Iteration: k, Error: e", fcVM.py:1455: one per Newton
+    iteration).  Returns (seconds for the ``steps`` iterations, seconds of set-up before the first iteration:
+    numba compilation, calcGSM, the sparse factorisation and the elastic solve)."""
+    import time
+    ref = load()
+    fix = numba_fix(model.fix)
+    m = model
+    t0 = time.perf_counter()
+    out = ref.calcGSM(m.elNodes, m.nocoord, m.materialbyElement, fix, ctl.grav_x, ctl.grav_y, ctl.grav_z,
+                      m.loadfaces, m.pressure, m.loadvertices, m.vertexloads, m.loadedges, m.edgeloads,
+                      m.loadfaces_uni, m.faceloads)
+    stm, row, col, glv, modf, V, lsx, lsy, lsz, ne, nn, x = out
+    stamps = []
+
+    def prn(*a):
+        msg = "".join(str(o) for o in a)
+        if msg.startswith("Iteration:") and int(msg.split(",")[0].split(":")[1]) >= 1:
+            stamps.append(time.perf_counter())
+            if len(stamps) == warmup + steps:
+                raise _StopTiming()
+
+    ref.prn_upd = prn
+    ref.plot = lambda *a, **k: (False,) + tuple(a[8:11])          # "stop" if the sweep ends first
+    win = _Window(ctl.csr_option == "CSR")
+    try:
+        ref.calcDisp(m.elNodes, m.nocoord.copy(), m.fixdof, m.movdof, modf, m.materialbyElement, stm, row, col, glv,
+                     ctl.nstep, ctl.iterat_max, ctl.error_max, ctl.relax, ctl.scale_re, ctl.scale_up, ctl.scale_dn,
+                     ctl.sig_yield, ctl.disp_output, ctl.ultimate_strain, win, ctl.Et_E, ctl.target_LF, x, m.noce, fix,
+                     ctl.grav_x, ctl.grav_y, ctl.grav_z, m.loadfaces, m.pressure, m.loadvertices, m.vertexloads,
+                     m.loadedges, m.edgeloads, m.loadfaces_uni, m.faceloads, ctl.gnl, ctl.maxImp, ctl.ev1, ctl.ev2)
+    except _StopTiming:
+        pass
+    if len(stamps) < warmup + steps:
+        raise RuntimeError(f"the reference's load sweep ended after {len(stamps)} Newton iterations, fewer than "
+                           f"warmup+steps = {warmup + steps}")
+    return stamps[warmup + steps - 1] - stamps[warmup - 1], stamps[0] - t0
