@@ -60,6 +60,7 @@ _SIGNATURES = {
     "fcvm_element_matrices": [ctxp, c_int, c_void_p, c_double, c_void_p],
     "fcvm_export_csc_lower": [ctxp, i64p, i64p, i64p, f64p],
     "fcvm_spmv": [ctxp, c_void_p, c_void_p],
+    "fcvm_matfree_apply": [ctxp, c_void_p, c_void_p],
     "fcvm_set_deflation": [ctxp, c_int, c_int, c_int, POINTER(ctypes.c_int32), f64p, f64p, u8p],
     "fcvm_pcg_solve": [ctxp, c_void_p, c_void_p, c_double, c_int, c_int, POINTER(c_int), f64p],
     "fcvm_pcg_phase_times": [ctxp, f64p, i64p, c_int],

@@ -114,6 +114,8 @@ struct fcvm_ctx {
   double *cooK = nullptr;       // [55][ne][9] element stiffness blocks (lower block triangle)
   double *minv = nullptr;       // [nn][9] inverse diagonal blocks
   bool assembled = false;
+  bool matrix_elastic = false;  // the assembled operator is calcGSM's elastic one: the PCG may apply it matrix-free
+  uint32_t *emask = nullptr;    // [ne] bit 3k+c: dof c of local node k prescribed (matrix-free product)
 
   // PCG work vectors
   double *pcg_r = nullptr, *pcg_z = nullptr, *pcg_p = nullptr, *pcg_q = nullptr, *pcg_s = nullptr;

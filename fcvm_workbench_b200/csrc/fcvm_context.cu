@@ -307,6 +307,7 @@ extern "C" int fcvm_create(fcvm_ctx **out, int device) {
 }
 
 namespace fcvm {
+int matfree_set_constraints(fcvm_ctx *c);
 void deflation_free(fcvm_ctx *c);
 void fused_free_mesh(fcvm_ctx *c);
 }
@@ -326,6 +327,7 @@ static void free_mesh(fcvm_ctx *c) {
   dfree(c->pcg_r); dfree(c->pcg_z); dfree(c->pcg_p); dfree(c->pcg_q); dfree(c->pcg_s); dfree(c->spmv_part);
   dfree(c->dof_weight); dfree(c->if_node); dfree(c->if_slot); dfree(c->if_buf);
   dfree(c->bslices); dfree(c->islices); dfree(c->tail3);
+  dfree(c->emask);
   dfree(c->h_du); dfree(c->h_disp); dfree(c->h_qin); dfree(c->diag9); dfree(c->gp_tmp);
   c->assembled = false;
   c->have_bcs = false;
@@ -585,12 +587,17 @@ extern "C" int fcvm_set_constraints(fcvm_ctx *c, const uint8_t *fixmask, const d
     fixdof[i] = fixmask[i] ? 0.0 : 1.0;
     mov[i] = (fixmask[i] && fixval[i] != 0.0) ? 1.0 : 0.0;      // movdof, fcVM.py:256-258
   }
+  // a value on a free dof means nothing (modf = K * fixval would pick it up): only prescribed dofs carry one
+  std::vector<double> val((size_t)n3);
+  for (int64_t i = 0; i < n3; i++) val[i] = fixmask[i] ? fixval[i] : 0.0;
   FCVM_CUDA(cudaMemcpy(c->fixmask, fixmask, n3, cudaMemcpyHostToDevice));
-  FCVM_CUDA(cudaMemcpy(c->fixval, fixval, sizeof(double) * n3, cudaMemcpyHostToDevice));
+  FCVM_CUDA(cudaMemcpy(c->fixval, val.data(), sizeof(double) * n3, cudaMemcpyHostToDevice));
   FCVM_CUDA(cudaMemcpy(c->movmask, mov.data(), sizeof(double) * n3, cudaMemcpyHostToDevice));
   FCVM_CUDA(cudaMemcpy(c->buf[FCVM_BUF_FIXDOF], fixdof.data(), sizeof(double) * n3, cudaMemcpyHostToDevice));
   c->have_bcs = true;
   c->assembled = false;
+  c->matrix_elastic = false;
+  FCVM_TRY(matfree_set_constraints(c));
   // the sparsity of K Z (which blocks vanish) depends on the prescribed dofs: rebuilt at the next assembly
   c->defl_structure = false;
   c->defl_ready = false;

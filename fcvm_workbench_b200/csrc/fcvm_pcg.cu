@@ -272,6 +272,10 @@ extern "C" int fcvm_spmv(fcvm_ctx *c, const double *x, double *y) {
 }
 
 namespace fcvm {
+bool matfree_active(const fcvm_ctx *c);
+int64_t matfree_parts(const fcvm_ctx *c);
+int launch_matfree(fcvm_ctx *c, const double *x, double *y, const double *sc, int rr_slot, int iters_slot, int thr_slot,
+                   double *dot_part, const double *rvec, double *dot_part2);
 bool pcg_fused_enabled(const fcvm_ctx *c);
 int pcg_fused_loop(fcvm_ctx *c, double *x, int max_iter);
 int interface_sum_on_comm_stream(fcvm_ctx *c, double *v);
@@ -297,6 +301,7 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
   }
   double *r = c->pcg_r, *u = c->pcg_z, *p = c->pcg_p, *wv = c->pcg_q, *s = c->pcg_s;
   const bool defl = c->defl_ready;
+  const bool mfree = matfree_active(c);
   double *part2 = defl ? c->spmv_part2 : nullptr;
   const double *q0 = nullptr;
   if (use_x0) {
@@ -340,7 +345,11 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
       ProfScope ps(c, 3);
       FCVM_TRY(deflation_correct(c, r, u, u, u, sc, S_ITERS));
     }
-    if (!multi) {
+    if (!multi && mfree) {
+      // elastic operator recomputed element by element instead of streaming the assembled matrix
+      ProfScope ps(c, 0);
+      FCVM_TRY(launch_matfree(c, u, wv, sc, flag, S_ITERS, S_THR, c->spmv_part, r, part2));
+    } else if (!multi) {
       ProfScope ps(c, 0);
       spmv_launch(c, u, wv, sc, flag, c->spmv_part, nullptr, -1, r, part2);
     } else {
@@ -360,7 +369,7 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
     }
     {
       ProfScope ps(c, 3);
-      k_dot_finish<<<1, 1024, 0, st>>>(c->nslices, c->spmv_part, part2, sc, multi ? L_WU : S_DELTA,
+      k_dot_finish<<<1, 1024, 0, st>>>(mfree ? matfree_parts(c) : c->nslices, c->spmv_part, part2, sc, multi ? L_WU : S_DELTA,
                                        multi ? -1 : S_GAMMA + (it_next & 1), multi ? c->tail3 : nullptr);
     }
     c->launches += 2;

@@ -402,6 +402,7 @@ extern "C" int fcvm_assemble(fcvm_ctx *c, int tangent, const double *disp, doubl
   FCVM_CUDA(cudaGetLastError());
   // modf needs the unconstrained operator: K * u_fix before rows/columns are eliminated
   c->assembled = true;
+  c->matrix_elastic = !tangent && disp == nullptr;
   FCVM_TRY(launch_spmv(c, c->fixval, c->pcg_q));
   FCVM_TRY(fcvm_interface_sum(c, c->pcg_q));
   k_apply_constraints<<<(unsigned)c->nslices, SELL_C, 0, c->stream>>>(c->nslices, c->slice_ptr, c->slot_node,

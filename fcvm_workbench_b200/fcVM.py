@@ -301,6 +301,10 @@ class Engine:
     def spmv(self, x, y):
         call("fcvm_spmv", self._ctx, ctypes.c_void_p(x), ctypes.c_void_p(y))
 
+    def matfree_apply(self, x, y):
+        """y = K x with the elastic operator recomputed element by element (what the PCG uses for GNLN)."""
+        call("fcvm_matfree_apply", self._ctx, ctypes.c_void_p(x), ctypes.c_void_p(y))
+
     def solve(self, b, x, rtol=1e-10, max_iter=20000, use_x0=False, raise_on_noconv=True):
         """x = K^-1 b by block-Jacobi PCG.  Returns (iterations, relative residual)."""
         it = ctypes.c_int()

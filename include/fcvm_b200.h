@@ -137,6 +137,11 @@ int fcvm_element_matrices(fcvm_ctx *ctx, int tangent, const double *disp, double
 int fcvm_export_csc_lower(fcvm_ctx *ctx, int64_t *nnz, int64_t *indptr, int64_t *indices, double *data);
 /* y = K x with the assembled matrix (block-SELL SpMV). */
 int fcvm_spmv(fcvm_ctx *ctx, const double *x, double *y);
+/* y = K x with calcGSM's elastic operator (constraints eliminated as in fcvm_assemble) recomputed element by
+ * element from the mesh instead of read from the assembled matrix: the product the PCG uses in the geometrically
+ * linear analysis.  Needs the mesh and the constraints only; equals fcvm_spmv after an elastic fcvm_assemble to
+ * round-off. */
+int fcvm_matfree_apply(fcvm_ctx *ctx, const double *x, double *y);
 
 /* ---- linear solve: replaces factor = cholesky(gsm); x = factor(b) (fcVM.py:1121-1135, 1401) -- */
 /* Preconditioned CG on the device (single-reduction form; block-Jacobi, plus the deflation level below

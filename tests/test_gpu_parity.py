@@ -264,6 +264,25 @@ def test_collapse_analysis_vs_oracle_larger_mesh(fc, oracle):
     assert 0 < o["pgp"].sum() < o["pgp"].size
 
 
+@pytest.mark.parametrize("n,mode", [(1, "platen"), (3, "platen"), (4, "tension"), (5, "punch")])
+def test_matrix_free_product_equals_assembled_spmv(fc, n, mode):
+    """The element-by-element product the PCG uses for the elastic operator against the assembled block-SELL
+    SpMV (itself held to the reference's matrix by the tests above): curved elements, prescribed dofs with
+    non-zero entries in x (constrained rows = element count * x, eliminated columns), ragged tile sizes."""
+    m, rng = distorted_cube(n, seed=11 + n, mode=mode)
+    with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+        glv = eng.vec()
+        eng.assemble(glv)
+        xh = rng.normal(size=eng.ndof)
+        x, y0, y1 = eng.vec(host=xh), eng.vec(), eng.vec()
+        eng.spmv(x, y0)
+        eng.matfree_apply(x, y1)
+        a, b = eng.get(y0), eng.get(y1)
+        assert np.abs(a - b).max() < 1e-12 * np.abs(a).max()
+        eng.matfree_apply(x, y0)                       # bit-reproducible
+        assert np.array_equal(eng.get(y0), b)
+
+
 def test_size_independent_properties_at_scale(fc):
     """At a size the oracle would take minutes for: symmetry of the operator, equilibrium of the
     internal force vector (sum of nodal forces of a self-equilibrated stress field is zero) and
