@@ -116,6 +116,9 @@ struct fcvm_ctx {
   bool assembled = false;
   bool matrix_elastic = false;  // the assembled operator is calcGSM's elastic one: the PCG may apply it matrix-free
   uint32_t *emask = nullptr;    // [ne] bit 3k+c: dof c of local node k prescribed (matrix-free product)
+  double *egeo = nullptr;       // [10][ne] inverse Jacobian (9) and w|J| (1) of the straight-sided elements
+  uint8_t *tile_affine = nullptr; // [ceil(ne/32)] all elements of the 32-element tile are straight-sided
+  int64_t n_affine_tiles = 0;
 
   // PCG work vectors
   double *pcg_r = nullptr, *pcg_z = nullptr, *pcg_p = nullptr, *pcg_q = nullptr, *pcg_s = nullptr;

@@ -308,6 +308,7 @@ extern "C" int fcvm_create(fcvm_ctx **out, int device) {
 
 namespace fcvm {
 int matfree_set_constraints(fcvm_ctx *c);
+int matfree_set_mesh(fcvm_ctx *c);
 void deflation_free(fcvm_ctx *c);
 void fused_free_mesh(fcvm_ctx *c);
 }
@@ -327,7 +328,8 @@ static void free_mesh(fcvm_ctx *c) {
   dfree(c->pcg_r); dfree(c->pcg_z); dfree(c->pcg_p); dfree(c->pcg_q); dfree(c->pcg_s); dfree(c->spmv_part);
   dfree(c->dof_weight); dfree(c->if_node); dfree(c->if_slot); dfree(c->if_buf);
   dfree(c->bslices); dfree(c->islices); dfree(c->tail3);
-  dfree(c->emask);
+  dfree(c->emask); dfree(c->egeo); dfree(c->tile_affine);
+  c->n_affine_tiles = 0;
   dfree(c->h_du); dfree(c->h_disp); dfree(c->h_qin); dfree(c->diag9); dfree(c->gp_tmp);
   c->assembled = false;
   c->have_bcs = false;
@@ -576,7 +578,7 @@ extern "C" int fcvm_set_mesh(fcvm_ctx *c, int64_t ne, int64_t nn, const int64_t 
   FCVM_CUDA(cudaGetLastError());
   cudaFree(blk_key); cudaFree(first_real);
   FCVM_TRY(dalloc(&c->cooK, (int64_t)55 * 9 * ne));
-  return FCVM_OK;
+  return matfree_set_mesh(c);
 }
 
 extern "C" int fcvm_set_constraints(fcvm_ctx *c, const uint8_t *fixmask, const double *fixval) {

@@ -138,9 +138,10 @@ __global__ void k_mirror(int64_t n, const double *__restrict__ L, double *__rest
 }
 
 // rhs_c = sum_{i in c} w_i Z_i^T r_i  -  sum_{(i,t) -> c} (K Z)_(i,t)^T y_i        (one block per cluster)
+template <typename CT>
 __global__ void __launch_bounds__(256)
 k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restrict__ cl_nodes,
-             const int32_t *__restrict__ ent_ptr, const int32_t *__restrict__ ent_node, const double *__restrict__ kzs,
+             const int32_t *__restrict__ ent_ptr, const int32_t *__restrict__ ent_node, const CT *__restrict__ kzs,
              int64_t nent,
              const double *__restrict__ xyz, const double *__restrict__ fixdof, const double *__restrict__ wt,
              const double *__restrict__ r, const double *__restrict__ y, double *__restrict__ rhs,
@@ -159,13 +160,34 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
   }
   if (y) {
     // entries of this box: consecutive lanes read consecutive doubles of each of the 18 component planes
-    for (int32_t idx = ent_ptr[c] + threadIdx.x; idx < ent_ptr[c + 1]; idx += 256) {
+    // two entries per trip: the dependent chains (entry -> node -> y) of both are in flight together
+    const int32_t e1 = ent_ptr[c + 1];
+    int32_t idx = ent_ptr[c] + threadIdx.x;
+    for (; idx + 256 < e1; idx += 512) {
+      const int64_t i = ent_node[idx], j = ent_node[idx + 256];
+      const CT *kz = kzs + idx;
+      const double y0 = y[3 * i], y1 = y[3 * i + 1], y2 = y[3 * i + 2];
+      const double z0 = y[3 * j], z1 = y[3 * j + 1], z2 = y[3 * j + 2];
+      double ka[18], kb[18];
+#pragma unroll
+      for (int q = 0; q < 18; q++) {
+        ka[q] = (double)__ldcs(kz + q * nent);
+        kb[q] = (double)__ldcs(kz + q * nent + 256);
+      }
+#pragma unroll
+      for (int m = 0; m < 6; m++) {
+        v[m] -= ka[m] * y0 + ka[6 + m] * y1 + ka[12 + m] * y2;
+        v[m] -= kb[m] * z0 + kb[6 + m] * z1 + kb[12 + m] * z2;
+      }
+    }
+    for (; idx < e1; idx += 256) {
       const int64_t i = ent_node[idx];
-      const double *kz = kzs + idx;
+      const CT *kz = kzs + idx;
       const double y0 = y[3 * i], y1 = y[3 * i + 1], y2 = y[3 * i + 2];
 #pragma unroll
       for (int m = 0; m < 6; m++)
-        v[m] -= __ldcs(kz + m * nent) * y0 + __ldcs(kz + (6 + m) * nent) * y1 + __ldcs(kz + (12 + m) * nent) * y2;
+        v[m] -= (double)__ldcs(kz + m * nent) * y0 + (double)__ldcs(kz + (6 + m) * nent) * y1 +
+                (double)__ldcs(kz + (12 + m) * nent) * y2;
     }
   }
   __shared__ double sm[6][8];
@@ -184,18 +206,34 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
   }
 }
 
-// lam = Einv rhs for rows [row0, row1): one warp per row, fixed order
+// lam = Einv rhs for rows [row0, row1): four warps per row (a quarter of the columns each, four loads in flight
+// per lane), partial sums added in warp order -- one warp per row left every warp with 48 dependent trips to HBM
+template <typename CT>
 __global__ void __launch_bounds__(256)
-k_gemv(int64_t n, int64_t row0, int64_t row1, const double *__restrict__ A, const double *__restrict__ x,
+k_gemv(int64_t n, int64_t row0, int64_t row1, const CT *__restrict__ A, const double *__restrict__ x,
        double *__restrict__ y, const double *__restrict__ sc, int done_slot) {
   if (sc && sc[done_slot] >= 0.0) return;
-  const int64_t row = row0 + blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= row1) return;
-  const int lane = threadIdx.x & 31;
+  __shared__ double part[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, quarter = warp & 3;
+  const int64_t row = row0 + blockIdx.x * 2 + (warp >> 2);
   double s = 0.0;
-  for (int64_t q = lane; q < n; q += 32) s += A[row * n + q] * x[q];
-  s = warp_sum(s);
-  if (lane == 0) y[row] = s;
+  if (row < row1) {
+    const CT *a = A + row * n;
+    const int64_t c0 = quarter * n / 4, c1 = (quarter + 1) * n / 4;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int64_t q = c0 + lane;
+    for (; q + 96 < c1; q += 128) {
+      s0 += (double)__ldcs(a + q) * x[q];
+      s1 += (double)__ldcs(a + q + 32) * x[q + 32];
+      s2 += (double)__ldcs(a + q + 64) * x[q + 64];
+      s3 += (double)__ldcs(a + q + 96) * x[q + 96];
+    }
+    for (; q < c1; q += 32) s0 += (double)__ldcs(a + q) * x[q];
+    s = warp_sum((s0 + s1) + (s2 + s3));
+  }
+  if (lane == 0) part[warp] = s;
+  __syncthreads();
+  if (row < row1 && quarter == 0 && lane == 0) y[row] = ((part[warp] + part[warp + 1]) + part[warp + 2]) + part[warp + 3];
 }
 
 // out_i = (base ? base_i : 0) + Z_i lam_(cluster of i)
@@ -278,6 +316,7 @@ namespace fcvm {
 int fused_build_items(fcvm_ctx *c, const std::vector<int32_t> &cl_ptr, const std::vector<int32_t> &ent_ptr);
 int fused_refresh_coarse(fcvm_ctx *c);
 void fused_free(fcvm_ctx *c);
+bool coarse_fp32();
 
 // K Z, E = Z^T K Z and its inverse for the matrix now in the context (called at the end of fcvm_assemble)
 int deflation_build(fcvm_ctx *c) {
@@ -397,18 +436,29 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
   const Grid g = grid_of(c);
   const double *fixdof = (const double *)c->buf[FCVM_BUF_FIXDOF];
   const int64_t n6 = 6 * c->ncl;
-  k_coarse_rhs<<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val, c->nent, c->xyz, fixdof,
-                                                c->dof_weight, r, y, c->d_rhs, sc, done_slot);
+  // the coarse operators only shape the preconditioner: single-precision copies halve their traffic
+  const bool f32 = coarse_fp32() && c->kz32 && c->einv32;
+  if (f32)
+    k_coarse_rhs<float><<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz32, c->nent, c->xyz,
+                                                         fixdof, c->dof_weight, r, y, c->d_rhs, sc, done_slot);
+  else
+    k_coarse_rhs<double><<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val, c->nent,
+                                                          c->xyz, fixdof, c->dof_weight, r, y, c->d_rhs, sc, done_slot);
   if (c->world > 1) {
     // every rank holds E^-1; each applies its own share of the rows and the shares are put together by an
     // all-reduce over a vector that is zero elsewhere (exact: x + 0 = x, so lam is identical on all ranks)
     FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_rhs, n6));
     const int64_t row0 = n6 * c->rank / c->world, row1 = n6 * (c->rank + 1) / c->world;
     FCVM_CUDA(cudaMemsetAsync(c->d_lam, 0, sizeof(double) * n6, st));
-    k_gemv<<<grid_for(row1 - row0, 8), 256, 0, st>>>(n6, row0, row1, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
+    if (f32)
+      k_gemv<float><<<grid_for(row1 - row0, 2), 256, 0, st>>>(n6, row0, row1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
+    else
+      k_gemv<double><<<grid_for(row1 - row0, 2), 256, 0, st>>>(n6, row0, row1, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
     FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_lam, n6));
+  } else if (f32) {
+    k_gemv<float><<<grid_for(n6, 2), 256, 0, st>>>(n6, 0, n6, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
   } else {
-    k_gemv<<<grid_for(n6, 8), 256, 0, st>>>(n6, 0, n6, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
+    k_gemv<double><<<grid_for(n6, 2), 256, 0, st>>>(n6, 0, n6, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
   }
   k_expand<<<grid_for(c->nn, 256), 256, 0, st>>>(c->nn, g, c->d_cid, c->xyz, fixdof, c->d_lam, base, out, sc, done_slot);
   c->launches += 3;

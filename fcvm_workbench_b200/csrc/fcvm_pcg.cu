@@ -185,7 +185,8 @@ __global__ void k_pcg_scalars(double rtol, double *sc) {
 // and the sums r.u (-> gamma_(it+1)) and r.r.  w = K u and delta = w.u come from the SpMV that follows.
 __global__ void __launch_bounds__(RED_THREADS)
 k_pcg_step(int64_t nn, int it, int defl, const double *__restrict__ w, const double *__restrict__ minv,
-           const double *__restrict__ wt_, double *x, double *r, double *u, double *p, double *s, double *red_part,
+           const double *__restrict__ wt_, double *__restrict__ x, double *__restrict__ r, double *__restrict__ u,
+           double *__restrict__ p, double *__restrict__ s, double *red_part,
            unsigned int *counter, double *sc, Slots<2> sl) {
   const int cur = it & 1, prv = cur ^ 1;
   if (sc[S_ITERS] >= 0.0) return;                    // converged earlier in this batch (sticky)
@@ -275,7 +276,8 @@ namespace fcvm {
 bool matfree_active(const fcvm_ctx *c);
 int64_t matfree_parts(const fcvm_ctx *c);
 int launch_matfree(fcvm_ctx *c, const double *x, double *y, const double *sc, int rr_slot, int iters_slot, int thr_slot,
-                   double *dot_part, const double *rvec, double *dot_part2);
+                   double *dot_part, const double *rvec, double *dot_part2, double *sc_out, int delta_slot,
+                   int gamma_slot);
 bool pcg_fused_enabled(const fcvm_ctx *c);
 int pcg_fused_loop(fcvm_ctx *c, double *x, int max_iter);
 int interface_sum_on_comm_stream(fcvm_ctx *c, double *v);
@@ -348,7 +350,9 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
     if (!multi && mfree) {
       // elastic operator recomputed element by element instead of streaming the assembled matrix
       ProfScope ps(c, 0);
-      FCVM_TRY(launch_matfree(c, u, wv, sc, flag, S_ITERS, S_THR, c->spmv_part, r, part2));
+      FCVM_TRY(launch_matfree(c, u, wv, sc, flag, S_ITERS, S_THR, c->spmv_part, r, part2, sc, S_DELTA,
+                              S_GAMMA + (it_next & 1)));
+      return FCVM_OK;                          // delta (and gamma) are published by the gather's last block
     } else if (!multi) {
       ProfScope ps(c, 0);
       spmv_launch(c, u, wv, sc, flag, c->spmv_part, nullptr, -1, r, part2);

@@ -403,14 +403,16 @@ int realloc_dev(T **p, int64_t n) {
   return FCVM_OK;
 }
 
+}  // namespace
+
+namespace fcvm {
+
+// K Z and E^-1 are streamed in single precision by default (they only shape the preconditioner);
+// FCVM_COARSE_FP64=1 keeps the double-precision copies (comparison runs)
 bool coarse_fp32() {
   static const bool v = !(getenv("FCVM_COARSE_FP64") && atoi(getenv("FCVM_COARSE_FP64")) != 0);
   return v;
 }
-
-}  // namespace
-
-namespace fcvm {
 
 // Opt-in (FCVM_PCG_FUSED=1): measured on B200 at 1M elements the persistent kernel is correct (the whole GPU suite
 // passes with it) but slower than one launch per phase -- 16 resident warps per SM at the 128 registers its

@@ -22,6 +22,6 @@ du, q = eng.vec(host=2e-3 * rng.normal(size=eng.ndof)), eng.vec()
 eng.gp_fill(fcVM.SIG_YIELD, 240.0)
 eng.update_stress_load(None, du, q, 0.0)             # k_stress_update, k_node_gather
 eng.update_peeq_csr(0.25, 0.0)                       # k_peeq_csr
-eng.solve(x, y, rtol=1e-30, max_iter=2, raise_on_noconv=False)   # k_pcg_*
+eng.solve(x, y, rtol=1e-30, max_iter=int(os.environ.get('PROFILE_ITERS', '2')), raise_on_noconv=False)   # k_pcg_*
 eng.synchronize()
 print("ok", eng.launch_count())
