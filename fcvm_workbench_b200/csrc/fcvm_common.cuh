@@ -116,6 +116,8 @@ struct fcvm_ctx {
   bool assembled = false;
   bool matrix_elastic = false;  // the assembled operator is calcGSM's elastic one: the PCG may apply it matrix-free
   uint32_t *emask = nullptr;    // [ne] bit 3k+c: dof c of local node k prescribed (matrix-free product)
+  unsigned int *ga_ticket = nullptr;  // [1 + groups] tickets of the gather's two-level dot-product finish (zero at rest)
+  double *ga_group_part = nullptr;    // [2][groups]
   double *egeo = nullptr;       // [10][ne] inverse Jacobian (9) and w|J| (1) of the straight-sided elements
   uint8_t *tile_affine = nullptr; // [ceil(ne/32)] all elements of the 32-element tile are straight-sided
   int64_t n_affine_tiles = 0;

@@ -274,12 +274,13 @@ k_elastic_apply_affine(int64_t ne, const int32_t *__restrict__ conn, const doubl
 // the dot-product partials of the block.  Nodes stay in their natural order -- walking them sorted by degree was
 // measured twice as slow (the locality of the element vectors is worth more than even warps).
 constexpr int GA_THREADS = 256;
+constexpr int GA_GROUP = 64;        // blocks per group of the two-level dot-product finish
 __global__ void __launch_bounds__(GA_THREADS)
 k_gather_apply(int64_t nn, const int32_t *__restrict__ n2e_ptr, const int32_t *__restrict__ n2e_idx,
                const double *__restrict__ elv, const uint8_t *__restrict__ fixmask, const double *__restrict__ x,
                double *__restrict__ y, const double *sc, int rr_slot, int iters_slot, int thr_slot,
                double *dot_part, const double *__restrict__ rvec, const double *__restrict__ wt, double *dot_part2,
-               unsigned int *ticket, double *sc_out, int delta_slot, int gamma_slot) {
+               unsigned int *ticket, double *group_part, double *sc_out, int delta_slot, int gamma_slot) {
   if (sc && (sc[iters_slot] >= 0.0 || sc[rr_slot] <= sc[thr_slot])) return;
   const int64_t d = blockIdx.x * (int64_t)GA_THREADS + threadIdx.x;
   double dsum = 0.0, rsum = 0.0;
@@ -324,19 +325,23 @@ k_gather_apply(int64_t nn, const int32_t *__restrict__ n2e_ptr, const int32_t *_
       if (dot_part2) dot_part2[blockIdx.x] = bsum;
     }
     if (ticket) {
-      // The block that finishes last adds the block partials in block order (a fixed shape whichever block it
-      // is) and publishes delta = y.x (and gamma = r.x): no separate reduction launch.
-      __shared__ bool last;
+      // Two-level finish without a separate launch and without a long serial tail: the block that completes a
+      // group of GA_GROUP blocks adds that group's partials, the block that completes the last group adds the
+      // group sums and publishes delta = y.x (and gamma = r.x).  The shape of the sums is fixed, whichever
+      // blocks happen to do them.
+      __shared__ int role;
+      const int grp = blockIdx.x / GA_GROUP, ngroups = (gridDim.x + GA_GROUP - 1) / GA_GROUP;
+      const int in_group = min(GA_GROUP, (int)gridDim.x - grp * GA_GROUP);
       if (threadIdx.x == 0) {
         __threadfence();
-        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+        role = (atomicAdd(ticket + 1 + grp, 1u) == (unsigned)(in_group - 1)) ? 1 : 0;
       }
       __syncthreads();
-      if (last) {
+      if (role) {
         double t = 0.0, g = 0.0;
-        for (int64_t i = threadIdx.x; i < gridDim.x; i += GA_THREADS) {
-          if (dot_part) t += __ldcg(dot_part + i);
-          if (dot_part2) g += __ldcg(dot_part2 + i);
+        if ((int)threadIdx.x < in_group) {
+          if (dot_part) t = __ldcg(dot_part + grp * GA_GROUP + threadIdx.x);
+          if (dot_part2) g = __ldcg(dot_part2 + grp * GA_GROUP + threadIdx.x);
         }
         t = warp_sum(t);
         g = warp_sum(g);
@@ -349,13 +354,43 @@ k_gather_apply(int64_t nn, const int32_t *__restrict__ n2e_ptr, const int32_t *_
         if (threadIdx.x == 0) {
           double tot = 0.0, gam = 0.0;
 #pragma unroll
-          for (int w = 0; w < GA_THREADS / 32; w++) {
+          for (int w = 0; w < GA_GROUP / 32; w++) {
             tot += sm[0][w];
             gam += sm[1][w];
           }
-          sc_out[delta_slot] = tot;
-          if (dot_part2 && gamma_slot >= 0) sc_out[gamma_slot] = gam;
-          *ticket = 0u;
+          group_part[grp] = tot;
+          group_part[ngroups + grp] = gam;
+          ticket[1 + grp] = 0u;
+          __threadfence();
+          role = (atomicAdd(ticket, 1u) == (unsigned)(ngroups - 1)) ? 2 : 1;
+        }
+        __syncthreads();
+        if (role == 2) {
+          t = 0.0;
+          g = 0.0;
+          for (int i = threadIdx.x; i < ngroups; i += GA_THREADS) {
+            t += __ldcg(group_part + i);
+            g += __ldcg(group_part + ngroups + i);
+          }
+          t = warp_sum(t);
+          g = warp_sum(g);
+          __syncthreads();
+          if (lane == 0) {
+            sm[0][warp] = t;
+            sm[1][warp] = g;
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            double tot = 0.0, gam = 0.0;
+#pragma unroll
+            for (int w = 0; w < GA_THREADS / 32; w++) {
+              tot += sm[0][w];
+              gam += sm[1][w];
+            }
+            sc_out[delta_slot] = tot;
+            if (dot_part2 && gamma_slot >= 0) sc_out[gamma_slot] = gam;
+            *ticket = 0u;
+          }
         }
       }
     }
@@ -365,6 +400,8 @@ k_gather_apply(int64_t nn, const int32_t *__restrict__ n2e_ptr, const int32_t *_
 }  // namespace
 
 namespace fcvm {
+
+int64_t matfree_parts(const fcvm_ctx *c) { return (3 * c->nn + GA_THREADS - 1) / GA_THREADS; }
 
 // per-mesh data of the matrix-free product: element geometry of the straight-sided elements
 int matfree_set_mesh(fcvm_ctx *c) {
@@ -388,6 +425,12 @@ int matfree_set_mesh(fcvm_ctx *c) {
 
 int matfree_set_constraints(fcvm_ctx *c) {
   if (!c->emask) FCVM_CUDA(cudaMalloc((void **)&c->emask, sizeof(uint32_t) * (size_t)c->ne));
+  if (!c->ga_ticket) {
+    const int64_t ngroups = (matfree_parts(c) + GA_GROUP - 1) / GA_GROUP;
+    FCVM_CUDA(cudaMalloc((void **)&c->ga_ticket, sizeof(unsigned int) * (size_t)(ngroups + 1)));
+    FCVM_CUDA(cudaMemsetAsync(c->ga_ticket, 0, sizeof(unsigned int) * (size_t)(ngroups + 1), c->stream));
+    FCVM_CUDA(cudaMalloc((void **)&c->ga_group_part, sizeof(double) * 2 * (size_t)ngroups));
+  }
   k_elem_mask<<<grid_for(c->ne, 256), 256, 0, c->stream>>>(c->ne, c->conn, c->fixmask, c->emask);
   c->launches++;
   FCVM_CUDA(cudaGetLastError());
@@ -401,7 +444,6 @@ bool matfree_active(const fcvm_ctx *c) {
   return !off && c->matrix_elastic && c->world == 1 && c->emask != nullptr;
 }
 
-int64_t matfree_parts(const fcvm_ctx *c) { return (3 * c->nn + GA_THREADS - 1) / GA_THREADS; }
 
 // y = K x; with sc: the early-out test of the PCG batch; dot_part / dot_part2: block partials of y.x and r.x;
 // with sc_out the last block of the gather also publishes their sums (delta, gamma)
@@ -423,7 +465,7 @@ int launch_matfree(fcvm_ctx *c, const double *x, double *y, const double *sc, in
                                                          rr_slot, iters_slot, thr_slot, aff ? c->tile_affine : nullptr);
   k_gather_apply<<<(unsigned)matfree_parts(c), GA_THREADS, 0, c->stream>>>(
       c->nn, c->n2e_ptr, c->n2e_idx, c->elv, c->fixmask, x, y, sc, rr_slot, iters_slot, thr_slot, dot_part, rvec,
-      c->dof_weight, dot_part2, sc_out ? c->red_counter + 2 : nullptr, sc_out, delta_slot, gamma_slot);
+      c->dof_weight, dot_part2, sc_out ? c->ga_ticket : nullptr, c->ga_group_part, sc_out, delta_slot, gamma_slot);
   c->launches += 2;
   FCVM_CUDA(cudaGetLastError());
   return FCVM_OK;
