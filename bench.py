@@ -232,6 +232,22 @@ def kernel_report(eng, model, prof, hbm_peak, world=1):
     return rep, alg
 
 
+class _StdoutToStderr:
+    """The reference prints its progress on stdout (also from numba-compiled code, i.e. through the C stream):
+    keep this process's stdout for the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 def cpu_baseline(W, K, n):
     """The reference's CPU path on a bounded sample of the same workload, timed on this box's host cores.
 
@@ -249,7 +265,8 @@ def cpu_baseline(W, K, n):
         have_ref = False
     if have_ref:
         import numba
-        dt, setup = rh.time_reference(m, c, W, K)
+        with _StdoutToStderr():
+            dt, setup = rh.time_reference(m, c, W, K)
         kind = "reference"
         what = (f"the unmodified reference (numba {numba.__version__}, its jitted element routines are serial: "
                 f"NUMBA_NUM_THREADS={threads or numba.config.NUMBA_NUM_THREADS} has no effect) + its calcDisp; "

@@ -302,12 +302,18 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
     FCVM_CUDA(cudaMemsetAsync(c->spmv_part, 0, sizeof(double) * (size_t)(c->nslices + 8), st));
   }
   double *r = c->pcg_r, *u = c->pcg_z, *p = c->pcg_p, *wv = c->pcg_q, *s = c->pcg_s;
-  const bool defl = c->defl_ready;
   const bool mfree = matfree_active(c);
+  const bool defl = c->defl_ready;
   double *part2 = defl ? c->spmv_part2 : nullptr;
   const double *q0 = nullptr;
+  // K x for the start vectors: the same operator the iteration uses
+  auto apply = [&](const double *xin, double *yout) -> int {
+    if (!mfree) return fcvm_spmv(c, xin, yout);
+    ProfScope ps(c, 0);
+    return launch_matfree(c, xin, yout, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, 0);
+  };
   if (use_x0) {
-    FCVM_TRY(fcvm_spmv(c, x, wv));
+    FCVM_TRY(apply(x, wv));
     q0 = wv;
   } else {
     FCVM_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n3, st));
@@ -324,7 +330,7 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
   if (defl) {
     // start from x + Z E^-1 Z^T (b - K x): the residual of the deflated iteration is orthogonal to Z
     FCVM_TRY(deflation_correct(c, r, nullptr, x, x, nullptr, 0));
-    FCVM_TRY(fcvm_spmv(c, x, wv));
+    FCVM_TRY(apply(x, wv));
     q0 = wv;
     FCVM_TRY(init());
   }
