@@ -73,6 +73,10 @@ _SIGNATURES = {
     "fcvm_comm_allreduce_sum": [ctxp, c_void_p, c_int64],
     "fcvm_comm_allreduce_max": [ctxp, c_void_p, c_int64],
     "fcvm_set_un_nodes": [ctxp, c_int64],
+    "fcvm_p2p_create": [ctxp, c_int64, c_int64, c_void_p],
+    "fcvm_p2p_attach": [ctxp, c_void_p, c_int, POINTER(ctypes.c_int32), POINTER(ctypes.c_int32), POINTER(ctypes.c_int32),
+                        i64p, c_int, POINTER(ctypes.c_int32), POINTER(ctypes.c_int32), i64p],
+    "fcvm_p2p_interface_sum": [ctxp, c_void_p],
     "fcvm_interface_sum": [ctxp, c_void_p],
     "fcvm_host_alloc": [c_int64, POINTER(c_void_p)],
     "fcvm_host_free": [c_void_p],

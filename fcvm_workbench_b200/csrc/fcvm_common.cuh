@@ -63,6 +63,8 @@ struct ProfSample {
   cudaEvent_t e0, e1;
 };
 
+struct P2PState;                 // peer-memory exchange of the multi-GPU PCG (fcvm_p2p.cu)
+
 }  // namespace fcvm
 
 struct fcvm_ctx {
@@ -151,6 +153,8 @@ struct fcvm_ctx {
   int32_t *bslices = nullptr, *islices = nullptr;
   int64_t n_bslices = 0, n_islices = 0;
   double *tail3 = nullptr;      // [4] per-rank PCG sums on their way through the scalar all-reduce
+  fcvm::P2PState *p2p = nullptr; // arenas mapped between the ranks of one box (CUDA IPC over NVLink)
+  bool p2p_attached = false;
 
   // rigid-body-mode deflation of the PCG (fcvm_deflation.cu): box clusters of nodes, six modes each
   int dn[3] = {0, 0, 0};        // clusters per direction (0 = deflation off)

@@ -307,6 +307,7 @@ extern "C" int fcvm_create(fcvm_ctx **out, int device) {
 }
 
 namespace fcvm {
+void p2p_free(fcvm_ctx *c);
 int matfree_set_constraints(fcvm_ctx *c);
 int matfree_set_mesh(fcvm_ctx *c);
 void deflation_free(fcvm_ctx *c);
@@ -342,6 +343,7 @@ extern "C" int fcvm_destroy(fcvm_ctx *c) {
   if (!c) return FCVM_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  p2p_free(c);
   fcvm_comm_destroy_(c);
   free_mesh(c);
   dfree(c->red_part); dfree(c->red_out); dfree(c->red_counter); dfree(c->d_arg); dfree(c->d_arg_part);

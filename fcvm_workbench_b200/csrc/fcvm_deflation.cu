@@ -317,6 +317,9 @@ int fused_build_items(fcvm_ctx *c, const std::vector<int32_t> &cl_ptr, const std
 int fused_refresh_coarse(fcvm_ctx *c);
 void fused_free(fcvm_ctx *c);
 bool coarse_fp32();
+bool p2p_ready(const fcvm_ctx *c);
+int p2p_allreduce_sum(fcvm_ctx *c, double *v, int64_t n, const double *sc, int done_slot);
+int p2p_allgather_rows(fcvm_ctx *c, double *v, int64_t n, int64_t row0, int64_t row1, const double *sc, int done_slot);
 
 // K Z, E = Z^T K Z and its inverse for the matrix now in the context (called at the end of fcvm_assemble)
 int deflation_build(fcvm_ctx *c) {
@@ -445,16 +448,24 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
     k_coarse_rhs<double><<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val, c->nent,
                                                           c->xyz, fixdof, c->dof_weight, r, y, c->d_rhs, sc, done_slot);
   if (c->world > 1) {
-    // every rank holds E^-1; each applies its own share of the rows and the shares are put together by an
-    // all-reduce over a vector that is zero elsewhere (exact: x + 0 = x, so lam is identical on all ranks)
-    FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_rhs, n6));
+    // every rank holds E^-1 and applies its own share of the rows.  Inside one box the two collectives are
+    // peer-memory exchanges (fcvm_p2p.cu: sums in rank order, identical on all ranks); without mapped arenas
+    // NCCL all-reduces (the row shares put together over a vector that is zero elsewhere: x + 0 = x, exact)
+    const bool p2p = p2p_ready(c);
+    if (p2p)
+      FCVM_TRY(p2p_allreduce_sum(c, c->d_rhs, n6, sc, done_slot));
+    else
+      FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_rhs, n6));
     const int64_t row0 = n6 * c->rank / c->world, row1 = n6 * (c->rank + 1) / c->world;
-    FCVM_CUDA(cudaMemsetAsync(c->d_lam, 0, sizeof(double) * n6, st));
+    if (!p2p) FCVM_CUDA(cudaMemsetAsync(c->d_lam, 0, sizeof(double) * n6, st));
     if (f32)
       k_gemv<float><<<grid_for(row1 - row0, 2), 256, 0, st>>>(n6, row0, row1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
     else
       k_gemv<double><<<grid_for(row1 - row0, 2), 256, 0, st>>>(n6, row0, row1, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
-    FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_lam, n6));
+    if (p2p)
+      FCVM_TRY(p2p_allgather_rows(c, c->d_lam, n6, row0, row1, sc, done_slot));
+    else
+      FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_lam, n6));
   } else if (f32) {
     k_gemv<float><<<grid_for(n6, 2), 256, 0, st>>>(n6, 0, n6, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
   } else {

@@ -439,9 +439,12 @@ int matfree_set_constraints(fcvm_ctx *c) {
 
 // The assembled operator is the elastic one on the undeformed mesh and the product may be recomputed instead
 // of streamed.  FCVM_MATFREE=0 keeps the assembled SpMV everywhere (comparison runs).
+bool p2p_ready(const fcvm_ctx *c);
+
+// On a partitioned mesh the per-rank products are completed by the peer-memory halo (fcvm_p2p.cu).
 bool matfree_active(const fcvm_ctx *c) {
   static const bool off = getenv("FCVM_MATFREE") && atoi(getenv("FCVM_MATFREE")) == 0;
-  return !off && c->matrix_elastic && c->world == 1 && c->emask != nullptr;
+  return !off && c->matrix_elastic && (c->world == 1 || p2p_ready(c)) && c->emask != nullptr;
 }
 
 

@@ -278,6 +278,9 @@ int64_t matfree_parts(const fcvm_ctx *c);
 int launch_matfree(fcvm_ctx *c, const double *x, double *y, const double *sc, int rr_slot, int iters_slot, int thr_slot,
                    double *dot_part, const double *rvec, double *dot_part2, double *sc_out, int delta_slot,
                    int gamma_slot);
+bool p2p_ready(const fcvm_ctx *c);
+int p2p_halo(fcvm_ctx *c, double *v, double *sc, int gamma_slot, int rr_slot, bool with_scalars, bool done_check);
+int p2p_check(fcvm_ctx *c);
 bool pcg_fused_enabled(const fcvm_ctx *c);
 int pcg_fused_loop(fcvm_ctx *c, double *x, int max_iter);
 int interface_sum_on_comm_stream(fcvm_ctx *c, double *v);
@@ -310,7 +313,8 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
   auto apply = [&](const double *xin, double *yout) -> int {
     if (!mfree) return fcvm_spmv(c, xin, yout);
     ProfScope ps(c, 0);
-    return launch_matfree(c, xin, yout, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, 0);
+    FCVM_TRY(launch_matfree(c, xin, yout, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, 0));
+    return multi ? p2p_halo(c, yout, sc, -1, -1, false, false) : FCVM_OK;
   };
   if (use_x0) {
     FCVM_TRY(apply(x, wv));
@@ -353,7 +357,17 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
       ProfScope ps(c, 3);
       FCVM_TRY(deflation_correct(c, r, u, u, u, sc, S_ITERS));
     }
-    if (!multi && mfree) {
+    if (multi && mfree) {
+      // partitioned mesh inside one box: per-rank products, then ONE peer-memory exchange that completes the
+      // shared rows (neighbours only) and sums the three scalars of the iteration in rank order
+      {
+        ProfScope ps(c, 0);
+        FCVM_TRY(launch_matfree(c, u, wv, sc, flag, S_ITERS, S_THR, c->spmv_part, r, part2, sc, L_WU, defl ? L_RU : -1));
+      }
+      ProfScope ps(c, 3);
+      return p2p_halo(c, wv, sc, (it_next > 0 || defl) ? S_GAMMA + (it_next & 1) : -1,
+                      it_next > 0 ? S_RR + (it_next & 1) : -1, true, true);
+    } else if (!multi && mfree) {
       // elastic operator recomputed element by element instead of streaming the assembled matrix
       ProfScope ps(c, 0);
       FCVM_TRY(launch_matfree(c, u, wv, sc, flag, S_ITERS, S_THR, c->spmv_part, r, part2, sc, S_DELTA,
@@ -427,6 +441,7 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
     FCVM_CUDA(cudaGetLastError());
     FCVM_CUDA(cudaMemcpyAsync(c->h_scalars, sc, sizeof(double) * 16, cudaMemcpyDeviceToHost, st));
     FCVM_CUDA(cudaStreamSynchronize(st));
+    if (multi && p2p_ready(c)) FCVM_TRY(p2p_check(c));
     if ((int)c->h_scalars[S_STATUS] == PCG_BREAKDOWN) {
       it = (int)c->h_scalars[S_ITERS];
       break;

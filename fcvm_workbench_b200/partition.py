@@ -116,6 +116,69 @@ class Partition:
         slot = np.searchsorted(self.if_nodes, g[loc]).astype(np.int64)
         return w, loc, slot
 
+    def p2p_plan(self, rank: int):
+        """Neighbour-only exchange lists of one rank for the peer-memory halo (csrc/fcvm_p2p.cu).
+
+        ``peers``        ranks sharing at least one node with ``rank`` (ascending)
+        ``send_ptr/send_node``  per peer: local indices of the nodes shared with it, ascending global id -- the
+                         same order on both sides, so position k of the list is the same node for sender and receiver
+        ``remote_off``   per peer: where this rank's segment starts inside THAT peer's receive area (in nodes)
+        ``n_recv``       nodes of this rank's receive area (segments in ascending peer order)
+        ``if_node/if_ptr/if_src``  per local interface node: its contributions in ascending rank order -- -1 for
+                         the rank's own value, else the node offset inside the receive area.  Summing in that order
+                         gives bit-identical results on every rank that holds the node.
+        """
+        world = self.world
+        g = self.nodes[rank]
+        shared = {}                                            # peer -> sorted global ids shared with it
+        for q in range(world):
+            if q == rank:
+                continue
+            both = np.intersect1d(g, self.nodes[q], assume_unique=True)
+            if both.size:
+                shared[q] = both
+        peers = sorted(shared)
+
+        def seg_offsets(r):
+            off, acc = {}, 0
+            gr = self.nodes[r]
+            for q in range(world):
+                if q == r:
+                    continue
+                n = np.intersect1d(gr, self.nodes[q], assume_unique=True).size
+                if n:
+                    off[q] = acc
+                    acc += n
+            return off, acc
+
+        my_off, n_recv = seg_offsets(rank)
+        send_ptr = np.zeros(len(peers) + 1, dtype=np.int32)
+        send_node, remote_off = [], []
+        for k, q in enumerate(peers):
+            loc = np.searchsorted(g, shared[q]).astype(np.int32)
+            send_node.append(loc)
+            send_ptr[k + 1] = send_ptr[k] + loc.size
+            remote_off.append(seg_offsets(q)[0][rank])
+        mult = self.multiplicity[g]
+        if_node = np.nonzero(mult > 1)[0].astype(np.int32)
+        if_ptr = np.zeros(if_node.size + 1, dtype=np.int32)
+        # contributions per interface node, ascending rank
+        ranks_of = [[] for _ in range(if_node.size)]
+        pos_in = {q: np.searchsorted(shared[q], g[if_node]) for q in peers}
+        for q in peers:
+            here = np.isin(g[if_node], shared[q], assume_unique=True)
+            for i in np.nonzero(here)[0]:
+                ranks_of[i].append((q, my_off[q] + int(pos_in[q][i])))
+        if_src = []
+        for i in range(if_node.size):
+            ent = sorted(ranks_of[i] + [(rank, -1)])
+            if_src.extend(off for _, off in ent)
+            if_ptr[i + 1] = len(if_src)
+        return dict(peers=np.asarray(peers, dtype=np.int32), send_ptr=send_ptr,
+                    send_node=(np.concatenate(send_node) if send_node else np.zeros(0, dtype=np.int32)).astype(np.int32),
+                    remote_off=np.asarray(remote_off, dtype=np.int64), n_recv=int(n_recv), if_node=if_node,
+                    if_ptr=if_ptr, if_src=np.asarray(if_src, dtype=np.int64))
+
     def un_nodes(self, rank: int) -> int:
         """Nodes of this rank that enter ``un``: the reference leaves the last global node out."""
         g = self.nodes[rank]
@@ -185,7 +248,48 @@ class Comm:
             self.dist.broadcast_object_list(box, src=0)
             idb = (ctypes.c_ubyte * 128).from_buffer_copy(box[0])
             call("fcvm_comm_init", eng._ctx, ctypes.cast(idb, ctypes.c_void_p), self.rank, self.world)
+            self.p2p = self._attach_p2p(eng)
         _ = _lib
+
+    P2P_SLOT = 16400      # doubles per rank slot of the small exchanges (>= the 16384 coarse unknowns allowed)
+
+    def _attach_p2p(self, eng) -> bool:
+        """Peer-memory exchange of the PCG iteration (csrc/fcvm_p2p.cu) between the ranks of one box: arenas
+        mapped through CUDA IPC.  Every rank must take the same decision, so failures are agreed on before the
+        arenas are used; without them the NCCL path stays.  FCVM_P2P=0 switches it off."""
+        import ctypes
+        import os
+
+        from ._lib import FcvmError, call, i64p
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        ok = os.environ.get("FCVM_P2P", "1") != "0" and self.world <= 8
+        plan = self.part.p2p_plan(self.rank) if ok else None
+        handle = (ctypes.c_ubyte * 64)()
+        if ok:
+            try:
+                call("fcvm_p2p_create", eng._ctx, plan["n_recv"], self.P2P_SLOT, ctypes.cast(handle, ctypes.c_void_p))
+            except FcvmError:
+                ok = False
+        every = self.allgather((ok, bytes(handle)))
+        if not all(e[0] for e in every):
+            return False
+        blob = (ctypes.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(e[1] for e in every))
+        arr = {k: np.ascontiguousarray(plan[k]) for k in ("peers", "send_ptr", "send_node", "remote_off", "if_node",
+                                                         "if_ptr", "if_src")}
+        try:
+            call("fcvm_p2p_attach", eng._ctx, ctypes.cast(blob, ctypes.c_void_p), int(arr["peers"].size),
+                 arr["peers"].ctypes.data_as(i32p), arr["send_ptr"].ctypes.data_as(i32p),
+                 arr["send_node"].ctypes.data_as(i32p), arr["remote_off"].ctypes.data_as(i64p), int(arr["if_node"].size),
+                 arr["if_node"].ctypes.data_as(i32p), arr["if_ptr"].ctypes.data_as(i32p), arr["if_src"].ctypes.data_as(i64p))
+            good = True
+        except FcvmError as e:
+            import warnings
+            warnings.warn(f"peer-memory exchange not available, NCCL path kept: {e}")
+            good = False
+        # the arenas may only be used once EVERY rank has mapped them
+        if not all(self.allgather(good)):
+            raise FcvmError(-5, "peer-memory arenas mapped on some ranks only")
+        return True
 
     def allgather(self, obj):
         if self.world == 1:

@@ -193,6 +193,19 @@ int fcvm_set_un_nodes(fcvm_ctx *ctx, int64_t n);
  * internal-force gather). */
 int fcvm_interface_sum(fcvm_ctx *ctx, double *v);
 
+/* Peer-memory exchanges inside one box (CUDA IPC over NVLink): the halo of the PCG product between neighbouring
+ * ranks and the small all-to-all sums of the iteration, each ONE kernel that stores into the peers' mapped memory,
+ * flags, waits and adds in rank order -- instead of NCCL all-reduces over a dense global interface vector.
+ * fcvm_p2p_create allocates this rank's arena (room for n_recv_nodes received rows and slots of slot_n doubles)
+ * and returns its 64-byte IPC handle; fcvm_p2p_attach maps the peers' arenas (handles in rank order, world x 64
+ * bytes) and takes the exchange lists of Partition.p2p_plan.  Optional: without it the NCCL path is used. */
+int fcvm_p2p_create(fcvm_ctx *ctx, int64_t n_recv_nodes, int64_t slot_n, void *handle64);
+int fcvm_p2p_attach(fcvm_ctx *ctx, const void *handles, int npeers, const int32_t *peer_rank, const int32_t *send_ptr,
+                    const int32_t *send_node, const int64_t *remote_off, int n_if, const int32_t *if_node,
+                    const int32_t *if_ptr, const int64_t *if_src);
+/* v[shared nodes] = sum over ranks through the peer-memory halo (fcvm_interface_sum is the NCCL form). */
+int fcvm_p2p_interface_sum(fcvm_ctx *ctx, double *v);
+
 /* ---- HOST-buffer drop-ins with the reference's argument lists ----------------------------- */
 /* Page-locked host memory for the arrays handed to fcvm_host_* (pageable memory works too, at
  * roughly a third of the PCIe rate). */

@@ -161,3 +161,42 @@ def test_scattered_partition_with_many_ranks_per_node(oracle):
     assert np.allclose(wsum, 1.0, rtol=0, atol=1e-15)
     assert np.abs(q.ravel() - ref).max() < 1e-12 * np.abs(ref).max()
     assert abs(dot - np.dot(ref, ref)) < 1e-12 * np.dot(ref, ref)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5, 8])
+def test_p2p_plan_reproduces_the_global_interface_sum(world):
+    """The neighbour-only exchange lists of ``Partition.p2p_plan`` emulated in numpy: every rank pushes its rows
+    into the peers' receive areas, then adds the contributions of each interface node in ascending rank order.
+    The result must be the sum over all holders, bit-identical on every rank that holds the node."""
+    m = cube_model(3, nxyz=(3, 3, 5))
+    part = slab_partition(m, world)
+    rng = np.random.default_rng(world)
+    plans = [part.p2p_plan(r) for r in range(world)]
+    local = [rng.normal(size=(part.nodes[r].size, 3)) for r in range(world)]
+    total = np.zeros((m.nn, 3))
+    for r in range(world):
+        total[part.nodes[r]] += local[r]
+    recv = [np.full((p["n_recv"], 3), np.nan) for p in plans]
+    for r, p in enumerate(plans):
+        assert list(p["peers"]) == sorted(set(p["peers"])) and r not in p["peers"]
+        for k, q in enumerate(p["peers"]):
+            nodes = p["send_node"][p["send_ptr"][k]:p["send_ptr"][k + 1]]
+            assert (np.diff(part.nodes[r][nodes]) > 0).all()                   # ascending global id
+            off = int(p["remote_off"][k])
+            recv[q][off:off + nodes.size] = local[r][nodes]
+    out = []
+    for r, p in enumerate(plans):
+        v = local[r].copy()
+        for i, node in enumerate(p["if_node"]):
+            s = np.zeros(3)
+            for src in p["if_src"][p["if_ptr"][i]:p["if_ptr"][i + 1]]:
+                s = s + (local[r][node] if src < 0 else recv[r][src])
+            v[node] = s
+        assert not np.isnan(v).any()
+        out.append(v)
+        np.testing.assert_allclose(v, total[part.nodes[r]], rtol=0, atol=1e-13)
+    glob = {}
+    for r in range(world):                                                      # bit-identical across holders
+        for gid, row in zip(part.nodes[r], out[r]):
+            if part.multiplicity[gid] > 1:
+                assert glob.setdefault(int(gid), row.tobytes()) == row.tobytes()
