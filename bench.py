@@ -20,8 +20,13 @@ sweep driven through the HOST-buffer C ABI (hostpath.HostEngine: numpy arrays in
 memory, every heavy call pays its PCIe copies).  The matrix (2.95 GB) and the Gauss-point state
 (0.6 GB) are far larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
 
-For N > 1 (torchrun) the same 1M-element mesh is partitioned element-wise into N slabs (strong
-scaling); shared-node sums and PCG dot products go through NCCL.
+For N > 1 (torchrun) the same 1M-element mesh is partitioned element-wise into N slabs (``--scaling strong``,
+the default: BASELINE's "1M elements at 1/2/4/8 B200"); ``--scaling weak`` keeps 6 n^3 elements PER RANK instead (the
+mesh grows to n x n x 2n, n x 2n x 2n, 2n x 2n x 2n cells at 2/4/8 ranks: 8M elements at N = 8, BASELINE config 4) and
+``--n 110 --scaling strong`` is the strong sweep of the 8M mesh.  Inside the PCG iteration the ranks exchange through
+mapped peer memory (NVLink); everything else goes through NCCL.  Every line carries a ``check`` object (Newton
+residual trace, load and displacement history of the sweep); with a committed single-GPU trace of the same
+sweep (``profiles/check_*.json``) the run fails when its history differs by more than 1e-6.
 """
 from __future__ import annotations
 
@@ -54,15 +59,35 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=16, help="cube edge of the bounded CPU sample")
     ap.add_argument("--deflation", type=int, default=DEFLATION,
                     help="unknowns of the rigid-body-mode coarse level of the PCG preconditioner (0 = block-Jacobi only)")
+    ap.add_argument("--scaling", default="strong", choices=("strong", "weak"),
+                    help="N > 1: partition the 6 n^3 mesh (strong) or keep 6 n^3 elements per rank (weak)")
+    ap.add_argument("--write-check", action="store_true", help="N = 1: write profiles/check_<sweep>.json")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
 
-def workload(n):
+def weak_cells(n, world):
+    """cells per direction of the weak-scaling mesh: 6 n^3 elements per rank, doubled direction by direction"""
+    f = [1, 1, 1]
+    k, d = world, 2
+    while k > 1:
+        if k % 2:
+            raise SystemExit("--scaling weak needs a power-of-two number of ranks")
+        f[d] *= 2
+        d = (d - 1) % 3
+        k //= 2
+    return n * f[0], n * f[1], n * f[2]
+
+
+def workload(n, nxyz=None):
     from fcvm_workbench_b200.control import Control
     from fcvm_workbench_b200.mesh import cube_model
-    m = cube_model(n, size=10.0, mode="platen", top_disp=0.05)
+    if nxyz is None:
+        m = cube_model(n, size=10.0, mode="platen", top_disp=0.05)
+    else:
+        # same element size and the same nominal strain as the cube: the platen moves in proportion to the height
+        m = cube_model(n, size=10.0 * nxyz[0] / n, mode="platen", top_disp=0.05 * nxyz[2] / n, nxyz=nxyz)
     c = Control(sig_yield=240.0, nstep=10, iterat_max=20, error_max=1e-3, relax=1.2, target_LF=1.0, Et_E=0.0)
     return m, c
 
@@ -150,8 +175,10 @@ class Sweep:
         self.t0 = self.t1 = None
         self.launch0 = self.launch1 = 0
         self.pcg_its = []
+        self.errors = []
         self.bytes0 = (0, 0)
         self.prof = None
+        self.phases = ({}, 0)
 
     def _sync(self):
         self.eng.synchronize()
@@ -162,6 +189,7 @@ class Sweep:
     def hook(self, d):
         from fcvm_workbench_b200.fcVM import StopAnalysis
         it = d["iterat_tot"]
+        self.errors.append(float(d["error"]))
         dev = getattr(self.eng, "dev", self.eng)
         if it == self.W:
             self._sync()
@@ -200,36 +228,134 @@ def run_sweep(model, ctl, eng, W, K, rtol, barrier=None, profile_stride=0, defla
     return sw, out
 
 
-def kernel_report(eng, model, prof, hbm_peak, world=1):
+def kernel_report(eng, model, prof, hbm_peak, world=1, total_ms=None):
     """Algorithmic bytes per launch of each kernel family ('Kernels and their rooflines')."""
     st = eng.matrix_stats()
     ne, nn = eng.ne, eng.nn
+    defl = eng.deflation_grid is not None
+    ncl = int(np.prod(eng.deflation_grid)) if defl else 0
     alg = {
-        # real 3x3 blocks (72 B) + their column index (4 B) + x read + y written once
-        "spmv": st["blocks_real"] * 76 + 2 * 24 * nn,
+        # matrix-free product: conn 40 B + mask 4 B + stored geometry 80 B + element vector written 240 B per element;
+        # gather: element vectors read 240 B + node->element list 40 B per element, x, r read and y written per node
+        "product": ne * (40 + 4 + 80 + 240) + ne * (240 + 40) + nn * (3 * 24 + 3),
         # conn 40 B, sig_old 192 B + sig_yield 32 B read, sig_new + sig_test 384 B + pgp 4 B written,
         # nodal xyz + du read once (48 B per node), element force vector written (240 B)
         "stress_update": ne * (40 + 192 + 32 + 384 + 4 + 240) + nn * 48,
         # element force vectors read (240 B), node->element list (40 B), qin written (24 B per node)
         "node_gather": ne * (240 + 40) + nn * 24,
+        # w, u, p, s, x, r read, p, s, x, r, u written, inverse diagonal blocks read
+        "pcg_step": nn * (6 * 24 + 5 * 24 + 72),
+        # K Z streamed in single precision (18 x 4 B per entry; entries ~ 3.3 per node), r, y, xyz, fixdof per node
+        "coarse_rhs": int(nn * (3.3 * (72 + 4 + 24) + 4 * 24)) if defl else 0,
+        "coarse_product": 4 * (6 * ncl) ** 2 // max(world, 1),
+        "coarse_expand": nn * (24 + 24 + 24 + 4 + 24),
     }
+    flops = {"product": ne * 1900.0}
+    names = {"spmv": "product"}                     # family 0 = the PCG's product (matrix-free here)
     rep = {}
-    for k, (ms, timed, seen) in prof.items():
+    for k0, (ms, timed, seen) in prof.items():
         if timed == 0:
             continue
+        k = names.get(k0, k0)
+        if k == "pcg_vector":
+            k = "pcg_vector_scopes"
         avg = ms / timed
         r = {"avg_ms": round(avg, 5), "timed_launches": timed, "launches": seen}
-        if k == "spmv" and world > 1:
-            # a partitioned product is two launches (boundary slices, then interior slices overlapped with
-            # the interface exchange): the bytes of one product against the time of both
-            avg *= 2
-            r["launches_per_product"] = 2
-            r["avg_ms_per_product"] = round(avg, 5)
-        if k in alg:
+        if total_ms:
+            r["share"] = round(avg * seen / total_ms, 4)
+        if k in alg and alg[k]:
             gbs = alg[k] / avg / 1e6
             r.update(algorithmic_bytes=int(alg[k]), achieved_gbs=round(gbs, 1), frac_of_hbm_peak=round(gbs / hbm_peak, 4))
+        if k in flops:
+            r["fp64_tflops"] = round(flops[k] / avg / 1e9, 2)
         rep[k] = r
+    # the vector step is what remains of the "pcg_vector" scopes after the coarse level and the exchanges
     return rep, alg
+
+
+def sweep_check(a, world, nxyz, sw, out):
+    """What a reader needs to compare runs across N: the Newton residual after every iteration of the sweep and the
+    load / displacement history of the completed load steps -- compared with the committed single-GPU trace of the
+    same sweep when there is one (rc != 0 beyond 1e-6 on the histories)."""
+    chk = {"newton_residual_trace": [float(f"{e:.9e}") for e in sw.errors],
+           "newton_iters_per_step": [int(i) for i in out["iters"]],
+           "lout": [float(v) for v in out["lout"]], "un": [float(v) for v in out["un"]]}
+    tag = f"n{a.n}" + ("" if nxyz is None else "_weak%d" % world)
+    path = os.path.join(ROOT, "profiles", f"check_{tag}.json")
+    if a.write_check and world == 1:
+        with open(path, "w") as f:
+            json.dump(dict(chk, sweep=tag, pcg_rtol=a.rtol, steps=a.steps, warmup=a.warmup), f)
+    if os.path.isfile(path) and not a.write_check:
+        with open(path) as f:
+            ref = json.load(f)
+
+        def dev(x, y):
+            k = min(len(x), len(y))
+            x, y = np.asarray(x[:k], dtype=float), np.asarray(y[:k], dtype=float)
+            return float(np.abs(x - y).max(initial=0.0) / max(np.abs(y).max(initial=0.0), 1e-300)), k
+
+        d_l, k_l = dev(chk["lout"], ref["lout"])
+        d_u, k_u = dev(chk["un"], ref["un"])
+        d_e, k_e = dev(chk["newton_residual_trace"], ref["newton_residual_trace"])
+        k_i = min(len(chk["newton_iters_per_step"]), len(ref["newton_iters_per_step"]))
+        chk["vs_single_gpu"] = {"reference": os.path.relpath(path, ROOT), "lout_rel_diff": d_l, "un_rel_diff": d_u,
+                                "residual_trace_rel_diff": d_e, "points_compared": [k_l, k_u, k_e],
+                                "same_newton_iters": chk["newton_iters_per_step"][:k_i] == ref["newton_iters_per_step"][:k_i],
+                                "ok": bool(d_l < 1e-6 and d_u < 1e-6
+                                           and chk["newton_iters_per_step"][:k_i] == ref["newton_iters_per_step"][:k_i])}
+    return chk
+
+
+def extra_kernel_legs(eng, hbm_peak, reps=10):
+    """Kernels that the geometrically linear sweep runs once (assembly) or not at all (assembled SpMV, used by the
+    large-displacement branch): ``reps`` timed launches each, CUDA events around every launch, after the sweep."""
+    st = eng.matrix_stats()
+    ne, nn = eng.ne, eng.nn
+    glv = eng.vec()
+    x, y = eng.vec(host=np.random.default_rng(0).normal(size=eng.ndof)), eng.vec()
+    eng.profile(1)
+    for _ in range(reps):
+        eng.assemble(glv)
+        eng.spmv(x, y)
+    prof = eng.profile_get()
+    eng.profile(0)
+    alg = {"elem_stiffness": ne * (40 + 3960), "coo_reduce": st["blocks_real"] * 72 + 100 * ne * 76,
+           "spmv": st["blocks_real"] * 76 + 2 * 24 * nn}
+    flops = {"elem_stiffness": ne * 6500.0}            # ~6.5 kFLOP per element (4 Jacobians, 4 gradient tiles, 55 blocks)
+    rep = {}
+    for k in ("elem_stiffness", "coo_reduce", "spmv"):
+        ms, timed, seen = prof[k]
+        if not timed:
+            continue
+        avg = ms / timed
+        gbs = alg[k] / avg / 1e6
+        rep[k] = {"avg_ms": round(avg, 5), "timed_launches": timed, "algorithmic_bytes": int(alg[k]),
+                  "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 4)}
+        if k in flops:
+            rep[k]["fp64_tflops"] = round(flops[k] / avg / 1e9, 2)
+    rep["note"] = ("the sweep re-uses one assembly; spmv is the assembled block-SELL product (large-displacement branch, "
+                   "start vectors), the PCG of this sweep applies the operator matrix-free")
+    return rep
+
+
+def roofline_of(kern, hbm_peak, peak_src, n, world):
+    """The kernel family with the largest share of the timed region."""
+    fam = {k: v for k, v in kern.items() if k in ("product", "pcg_step", "coarse_rhs", "coarse_product", "stress_update")}
+    if not fam:
+        return None
+    top = max(fam, key=lambda k: fam[k]["avg_ms"] * fam[k]["launches"])
+    r = fam[top]
+    names = {"product": "k_elastic_apply_affine + k_gather_apply (matrix-free product w = K u of the PCG: element pass + "
+                        "deterministic gather with the fused dot products)",
+             "pcg_step": "k_pcg_step", "coarse_rhs": "k_coarse_rhs", "coarse_product": "k_gemv", "stress_update": "k_stress_update_pair"}
+    return {"kernel": names[top], "bound": "hbm", "achieved": r.get("achieved_gbs"), "peak": hbm_peak, "unit": "GB/s",
+            "frac": r.get("frac_of_hbm_peak"), "traffic": measured_traffic(top, n, world), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": r.get("algorithmic_bytes"), "avg_launch_ms": r.get("avg_ms"),
+            "share_of_timed_region": r.get("share"),
+            "note": ("FP64-issue bound, not HBM bound: ~1.9 kFLOP per element against 0.36 kB of algorithmic traffic; the "
+                     "assembled SpMV it replaces runs at the copy bandwidth (kernels_standalone.spmv) but moves 8x the bytes")
+            if top == "product" else None,
+            "fp64_tflops": r.get("fp64_tflops")}
 
 
 class _StdoutToStderr:
@@ -352,8 +478,13 @@ def main():
 
     hbm_peak, peak_src = peaks()
     t_mesh = time.time()
-    gmodel, ctl = workload(a.n)
+    nxyz = weak_cells(a.n, world) if (a.scaling == "weak" and world > 1) else None
+    gmodel, ctl = workload(a.n, nxyz)
     ne_total = gmodel.ne
+    defl_target = a.deflation
+    if a.deflation and ne_total > 1.5 * 6 * 55 ** 3:
+        # boxes of the same size as on the 1M cube as far as the dense coarse inverse allows (16384 unknowns)
+        defl_target = int(min(16380, a.deflation * ne_total / (6 * 55 ** 3)))
     if world > 1:
         part = partition.slab_partition(gmodel, world)
         model = part.local_model(rank)
@@ -366,7 +497,10 @@ def main():
     if rank == 0:
         clocks.start()
     eng = fcVM.Engine(model.elNodes, model.nocoord, model.materialbyElement, model.fix, device=local, comm=comm)
-    sw, out = run_sweep(model, ctl, eng, a.warmup, a.steps, a.rtol, barrier, profile_stride=31, deflation=a.deflation)
+    sw, out = run_sweep(model, ctl, eng, a.warmup, a.steps, a.rtol, barrier, profile_stride=31, deflation=defl_target)
+    p2p = bool(getattr(comm, "p2p", False)) if comm is not None else False
+    check = sweep_check(a, world, nxyz, sw, out)
+    extra = extra_kernel_legs(eng, hbm_peak) if world == 1 else {}
     defl_grid = eng.deflation_grid
     ms = sw.ms
     if world > 1:
@@ -374,7 +508,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clk = clocks.stop(sw.t0, sw.t1) if rank == 0 else None
-    kern, alg = kernel_report(eng, model, sw.prof, hbm_peak, world)
+    kern, alg = kernel_report(eng, model, sw.prof, hbm_peak, world, total_ms=sw.ms)
     launches = sw.launch1 - sw.launch0
     # raw Gauss-point update rate of the stress-update kernel + its deterministic force assembly
     gp_rate = None
@@ -387,7 +521,7 @@ def main():
     if not a.no_e2e:
         hcomm = partition.Comm(part, rank, world) if world > 1 else None
         heng = HostEngine(model.elNodes, model.nocoord, model.materialbyElement, model.fix, device=local, comm=hcomm)
-        hs, _ = run_sweep(model, ctl, heng, a.warmup, a.steps, a.rtol, barrier, deflation=a.deflation)
+        hs, _ = run_sweep(model, ctl, heng, a.warmup, a.steps, a.rtol, barrier, deflation=defl_target)
         hms, hb = hs.ms, [hs.bytes1[0] - hs.bytes0[0], hs.bytes1[1] - hs.bytes0[1]]
         if world > 1:
             t = torch.tensor([hms], device="cuda", dtype=torch.float64)
@@ -408,16 +542,21 @@ def main():
         cb = cpu_baseline(min(a.warmup, 3), min(a.steps, 10), a.cpu_n)
 
     if rank == 0:
-        spmv = kern.get("spmv", {})
         line = {
             "metric": METRIC, "value": 4 * ne_total * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"structured C3D10 cube n={a.n}: {ne_total} elements, {gmodel.nn} nodes, von Mises "
+            "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"structured C3D10 {'cube' if nxyz is None else 'block %dx%dx%d cells' % tuple(nxyz)} "
+                                   f"n={a.n}: {ne_total} elements, {gmodel.nn} nodes, von Mises "
                                    "(elastic-perfectly-plastic) platen compression, displacement-controlled load sweep",
                        "elements": ne_total, "nodes": gmodel.nn, "step": "one Newton iteration (PCG solve + arc-length "
                        "update + radial-return stress update + internal force + residual)",
-                       "pcg_rtol": a.rtol, "partition": f"{world} element slab(s)",
+                       "pcg_rtol": a.rtol, "partition": f"{world} element slab(s)" + (
+                           f", {a.scaling} scaling" + (f" ({6 * a.n ** 3} elements per rank)" if a.scaling == "weak" else "")
+                           if world > 1 else ""),
+                       "exchange": ("peer memory over NVLink inside the PCG iteration (neighbour-only halo, rank-ordered "
+                                    "sums), NCCL elsewhere" if p2p else ("NCCL" if world > 1 else "none")),
+                       "product": "elastic operator recomputed element by element (matrix-free) inside the PCG",
                        "preconditioner": ("block-Jacobi + rigid-body-mode deflation, boxes %s" % (defl_grid,)
                                           if defl_grid else "block-Jacobi"),
                        "l2": "inputs exceed L2 (matrix 2.95 GB, Gauss-point state 0.6 GB vs 126 MB)"},
@@ -426,13 +565,10 @@ def main():
             "pcg_iterations_per_step": float(np.mean(sw.pcg_its)) if sw.pcg_its else None,
             "gpu_launches": int(launches),
             "e2e": e2e,
-            "roofline": {"kernel": "k_spmv_sell (block-SELL SpMV inside PCG, 4 warps per 32-row slice)", "bound": "hbm",
-                         "achieved": spmv.get("achieved_gbs"), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": spmv.get("frac_of_hbm_peak"), "traffic": measured_traffic("k_spmv_sell", a.n, world),
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": spmv.get("algorithmic_bytes"),
-                         "avg_launch_ms": spmv.get("avg_ms_per_product", spmv.get("avg_ms"))},
+            "roofline": roofline_of(kern, hbm_peak, peak_src, a.n, world),
             "kernels": kern,
+            "kernels_standalone": extra,
+            "check": check,
             "pcg_phases_ms_per_iteration": ({k: round(v / max(sw.phases[1], 1), 5) for k, v in sw.phases[0].items()}
                                             if sw.phases[1] else None),
             "cpu_baseline": cb,

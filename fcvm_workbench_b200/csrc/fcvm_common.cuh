@@ -42,7 +42,7 @@ constexpr int SELL_C = 32;           // rows per SELL slice = one warp
 constexpr int SELL_SIGMA = 4096;     // sorting window (rows)
 constexpr int RED_BLOCKS = 592;      // 4 x 148 SMs: fixed shape of every two-stage reduction
 constexpr int RED_THREADS = 256;
-constexpr int NUM_PROFILE = 7;
+constexpr int NUM_PROFILE = 12;
 
 // Gauss points of the 10-node tetrahedron (fcVM.py:589-596)
 constexpr double GP_A = 0.138196601125011;
@@ -214,7 +214,10 @@ struct ProfScope {
       cudaEventCreate(&e0);
       cudaEventCreate(&e1);
       cudaEventRecord(e0, c->stream);
-    } else if ((k % c->prof_stride) == 0 && c->prof_used < c->prof_pool.size()) {
+    } else if (((k % c->prof_stride) == 0 || which == 1 || which == 2 || (which >= 4 && which <= 6)) &&
+               c->prof_used < c->prof_pool.size()) {
+      // the families that run once per Newton iteration (or per assembly) are timed every time, the per-PCG-iteration
+      // ones every stride-th launch
       smp = &c->prof_pool[c->prof_used++];
       smp->which = which;
       cudaEventRecord(smp->e0, c->stream);

@@ -441,12 +441,15 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
   const int64_t n6 = 6 * c->ncl;
   // the coarse operators only shape the preconditioner: single-precision copies halve their traffic
   const bool f32 = coarse_fp32() && c->kz32 && c->einv32;
+  {
+  ProfScope ps8(c, 8);
   if (f32)
     k_coarse_rhs<float><<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz32, c->nent, c->xyz,
                                                          fixdof, c->dof_weight, r, y, c->d_rhs, sc, done_slot);
   else
     k_coarse_rhs<double><<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val, c->nent,
                                                           c->xyz, fixdof, c->dof_weight, r, y, c->d_rhs, sc, done_slot);
+  }
   if (c->world > 1) {
     // every rank holds E^-1 and applies its own share of the rows.  Inside one box the two collectives are
     // peer-memory exchanges (fcvm_p2p.cu: sums in rank order, identical on all ranks); without mapped arenas
@@ -458,19 +461,25 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
       FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_rhs, n6));
     const int64_t row0 = n6 * c->rank / c->world, row1 = n6 * (c->rank + 1) / c->world;
     if (!p2p) FCVM_CUDA(cudaMemsetAsync(c->d_lam, 0, sizeof(double) * n6, st));
-    if (f32)
-      k_gemv<float><<<grid_for(row1 - row0, 2), 256, 0, st>>>(n6, row0, row1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
-    else
-      k_gemv<double><<<grid_for(row1 - row0, 2), 256, 0, st>>>(n6, row0, row1, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
+    {
+      ProfScope ps9(c, 9);
+      if (f32)
+        k_gemv<float><<<grid_for(row1 - row0, 2), 256, 0, st>>>(n6, row0, row1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
+      else
+        k_gemv<double><<<grid_for(row1 - row0, 2), 256, 0, st>>>(n6, row0, row1, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
+    }
     if (p2p)
       FCVM_TRY(p2p_allgather_rows(c, c->d_lam, n6, row0, row1, sc, done_slot));
     else
       FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_lam, n6));
   } else if (f32) {
+    ProfScope ps9(c, 9);
     k_gemv<float><<<grid_for(n6, 2), 256, 0, st>>>(n6, 0, n6, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
   } else {
+    ProfScope ps9(c, 9);
     k_gemv<double><<<grid_for(n6, 2), 256, 0, st>>>(n6, 0, n6, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
   }
+  ProfScope ps10(c, 10);
   k_expand<<<grid_for(c->nn, 256), 256, 0, st>>>(c->nn, g, c->d_cid, c->xyz, fixdof, c->d_lam, base, out, sc, done_slot);
   c->launches += 3;
   FCVM_CUDA(cudaGetLastError());

@@ -13,10 +13,14 @@
 //   k_xchg_halo     rows of w = K u at shared nodes -- neighbours only (Partition.p2p_plan), not a dense global
 //                   interface vector -- together with the three per-rank scalars of the iteration
 //
-// Buffers are double-buffered by the parity of a DEVICE-side epoch counter that advances only when an exchange
-// really runs (all ranks skip the no-op launches after convergence together: the flag they test is itself a
-// bit-identical sum), so a peer can never overwrite data that is still being read.  A rank that waits longer
-// than ~20 s raises a status flag instead of hanging.  NCCL stays for everything outside the iteration.
+// Buffers are double-buffered by the parity of an epoch that every rank advances with every launch, so a peer
+// can never overwrite data that is still being read: to be two exchanges ahead it would need this rank's flag
+// of the exchange in between.  (The no-op launches after convergence are skipped by all ranks together -- the
+// flag they test is itself a bit-identical sum -- and the next real exchange follows a host synchronisation.)
+// A rank that waits longer than ~20 s raises a status flag instead of hanging.  NCCL stays for everything outside
+// the iteration.
+#include <algorithm>
+
 #include "fcvm_common.cuh"
 #include "fcvm_pcg.cuh"
 
@@ -29,7 +33,7 @@ constexpr int P2P_MAX_RANKS = 8;
 struct P2PDev {
   int world, rank, npeers, n_if;
   char *peer[P2P_MAX_RANKS];        // base of every rank's arena (peer[rank] = own)
-  unsigned long long off_flags, off_epoch, off_status, off_scal, off_slots, off_halo;
+  unsigned long long off_flags, off_ticket, off_status, off_scal, off_slots, off_halo;
   long long slot_n, halo_cap;       // doubles per slot, nodes per halo buffer
   const int32_t *peer_rank, *send_ptr, *send_node;
   const int64_t *remote_off;
@@ -45,6 +49,8 @@ struct P2PState {
   int32_t *peer_rank = nullptr, *send_ptr = nullptr, *send_node = nullptr, *if_node = nullptr, *if_ptr = nullptr;
   int64_t *remote_off = nullptr, *if_src = nullptr;
   unsigned long long *h_status = nullptr;   // pinned
+  int64_t n_send = 0;
+  unsigned long long epoch[2] = {0, 0};     // per channel, advanced by the host with every launch (all ranks alike)
 };
 
 }  // namespace fcvm
@@ -63,25 +69,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 constexpr long long SPIN_LIMIT = 40000000000LL;    // SM cycles (~20 s)
 constexpr int XT = 1024;
 
-// epoch of this exchange on channel ch (device-side counter: advances only when the exchange runs)
-__device__ __forceinline__ unsigned long long next_epoch(const P2PDev &d, int ch, unsigned long long *sh) {
-  if (threadIdx.x == 0) {
-    unsigned long long *e = (unsigned long long *)(d.peer[d.rank] + d.off_epoch) + ch;
-    *sh = ++(*e);
-  }
-  __syncthreads();
-  return *sh;
-}
-
-// publish epoch e on channel ch to the ranks listed (everyone, or the halo peers), then wait for theirs
-__device__ __forceinline__ bool signal_and_wait(const P2PDev &d, int ch, unsigned long long e, bool all_ranks, int *bad) {
-  __threadfence_system();
-  __syncthreads();
-  const int n = all_ranks ? d.world : d.npeers;
-  if ((int)threadIdx.x < n) {
-    const int q = all_ranks ? (int)threadIdx.x : d.peer_rank[threadIdx.x];
-    unsigned long long *theirs = (unsigned long long *)(d.peer[q] + d.off_flags) + ch * P2P_MAX_RANKS + d.rank;
-    st_release_sys(theirs, e);
+// publish epoch e on channel ch to every rank (the block whose `publish` is set), then wait for everyone's
+__device__ __forceinline__ bool signal_and_wait(const P2PDev &d, int ch, unsigned long long e, bool publish, int *bad) {
+  if ((int)threadIdx.x < d.world) {
+    const int q = (int)threadIdx.x;
+    if (publish) {
+      unsigned long long *theirs = (unsigned long long *)(d.peer[q] + d.off_flags) + ch * P2P_MAX_RANKS + d.rank;
+      st_release_sys(theirs, e);
+    }
     const unsigned long long *mine = (const unsigned long long *)(d.peer[d.rank] + d.off_flags) + ch * P2P_MAX_RANKS + q;
     const long long t0 = clock64();
     while (ld_acquire_sys(mine) < e) {
@@ -103,12 +98,11 @@ __device__ __forceinline__ bool signal_and_wait(const P2PDev &d, int ch, unsigne
 // MODE 1: every rank contributes src[seg0..seg1); out[0..n) = the assembled vector
 template <int MODE>
 __global__ void __launch_bounds__(XT)
-k_xchg(P2PDev d, const double *src, long long n, long long seg0, long long seg1, double *out, const double *sc, int done_slot) {
+k_xchg(P2PDev d, unsigned long long e, const double *src, long long n, long long seg0, long long seg1, double *out,
+       const double *sc, int done_slot) {
   if (sc && sc[done_slot] >= 0.0) return;            // every rank holds the same flag
-  __shared__ unsigned long long esh;
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;
-  const unsigned long long e = next_epoch(d, 0, &esh);
   const long long par = (long long)(e & 1ull);
   for (int p = 0; p < d.world; p++) {
     double *slots = (double *)(d.peer[p] + d.off_slots);
@@ -120,6 +114,8 @@ k_xchg(P2PDev d, const double *src, long long n, long long seg0, long long seg1,
       for (long long i = seg0 + threadIdx.x; i < seg1; i += XT) dst[i] = src[i];
     }
   }
+  __threadfence_system();
+  __syncthreads();
   if (!signal_and_wait(d, 0, e, true, &bad)) return;
   const double *mine = (const double *)(d.peer[d.rank] + d.off_slots) + par * d.world * d.slot_n;
   for (long long i = threadIdx.x; i < n; i += XT) {
@@ -134,33 +130,46 @@ k_xchg(P2PDev d, const double *src, long long n, long long seg0, long long seg1,
 }
 
 // v[shared nodes] = sum over the ranks that hold them (ascending rank); the three per-rank scalars of the
-// iteration (r.u, r.r, w.u in sc[L_RU], sc[L_RR], sc[L_WU]) are summed on the way and stored like k_tail_get did
-__global__ void __launch_bounds__(XT)
-k_xchg_halo(P2PDev d, double *v, double *sc, int gamma_slot, int rr_slot, int with_scalars, int done_check) {
+// iteration (r.u, r.r, w.u in sc[L_RU], sc[L_RR], sc[L_WU]) are summed on the way and stored like k_tail_get did.
+// Several blocks: all push, the block that finishes its pushes last (ticket) publishes the flags, every block
+// waits for the peers' flags itself and unpacks its share -- no grid barrier.
+constexpr int HT = 256;
+__global__ void __launch_bounds__(HT)
+k_xchg_halo(P2PDev d, unsigned long long e, double *v, double *sc, int gamma_slot, int rr_slot, int with_scalars, int done_check) {
   if (done_check && sc[S_ITERS] >= 0.0) return;
-  __shared__ unsigned long long esh;
-  __shared__ int bad;
+  __shared__ int bad, publish;
   if (threadIdx.x == 0) bad = 0;
-  const unsigned long long e = next_epoch(d, 1, &esh);
   const long long par = (long long)(e & 1ull);
+  const long long stride = (long long)gridDim.x * HT, t0 = blockIdx.x * (long long)HT + threadIdx.x;
   for (int pi = 0; pi < d.npeers; pi++) {
     const int q = d.peer_rank[pi];
     double *dst = (double *)(d.peer[q] + d.off_halo) + 3 * (par * d.halo_cap + d.remote_off[pi]);
     const int32_t k0 = d.send_ptr[pi], k1 = d.send_ptr[pi + 1];
-    for (long long i = threadIdx.x; i < 3LL * (k1 - k0); i += XT) {
+    for (long long i = t0; i < 3LL * (k1 - k0); i += stride) {
       const long long k = i / 3;
       const int c = (int)(i - 3 * k);
       dst[i] = v[3 * (long long)d.send_node[k0 + k] + c];
     }
   }
-  if (with_scalars && threadIdx.x < 3) {
+  if (with_scalars && blockIdx.x == 0 && threadIdx.x < 3) {
     const double val = sc[threadIdx.x == 0 ? L_RU : (threadIdx.x == 1 ? L_RR : L_WU)];
     for (int p = 0; p < d.world; p++) ((double *)(d.peer[p] + d.off_scal))[(par * P2P_MAX_RANKS + d.rank) * 4 + threadIdx.x] = val;
   }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int *ticket = (unsigned int *)(d.peer[d.rank] + d.off_ticket);
+    publish = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    if (publish) {
+      *ticket = 0u;
+      __threadfence_system();      // the other blocks' pushes (observed through the ticket) before the flags
+    }
+  }
+  __syncthreads();
   // the scalars go to every rank, the rows to the neighbours only: one flag round over all ranks covers both
-  if (!signal_and_wait(d, 1, e, true, &bad)) return;
+  if (!signal_and_wait(d, 1, e, publish != 0, &bad)) return;
   const double *halo = (const double *)(d.peer[d.rank] + d.off_halo) + 3 * par * d.halo_cap;
-  for (long long i = threadIdx.x; i < 3LL * d.n_if; i += XT) {
+  for (long long i = t0; i < 3LL * d.n_if; i += stride) {
     const long long k = i / 3;
     const int c = (int)(i - 3 * k);
     const long long node = d.if_node[k];
@@ -172,7 +181,7 @@ k_xchg_halo(P2PDev d, double *v, double *sc, int gamma_slot, int rr_slot, int wi
     }
     v[3 * node + c] = s;
   }
-  if (with_scalars && threadIdx.x < 3) {
+  if (with_scalars && blockIdx.x == 0 && threadIdx.x < 3) {
     const double *scal = (const double *)(d.peer[d.rank] + d.off_scal) + par * P2P_MAX_RANKS * 4;
     double s = 0.0;
     for (int r = 0; r < d.world; r++) s += __ldcg(scal + r * 4 + threadIdx.x);
@@ -199,7 +208,8 @@ bool p2p_ready(const fcvm_ctx *c) { return c->p2p != nullptr && c->p2p_attached;
 int p2p_allreduce_sum(fcvm_ctx *c, double *v, int64_t n, const double *sc, int done_slot) {
   P2PState *s = c->p2p;
   FCVM_CHECK(n <= s->d.slot_n, FCVM_E_ARG, "p2p exchange: %lld doubles exceed the slot size %lld", (long long)n, (long long)s->d.slot_n);
-  k_xchg<0><<<1, XT, 0, c->stream>>>(s->d, v, n, 0, 0, v, sc, done_slot);
+  ProfScope ps(c, 7);
+  k_xchg<0><<<1, XT, 0, c->stream>>>(s->d, ++s->epoch[0], v, n, 0, 0, v, sc, done_slot);
   c->launches++;
   FCVM_CUDA(cudaGetLastError());
   return FCVM_OK;
@@ -208,14 +218,20 @@ int p2p_allreduce_sum(fcvm_ctx *c, double *v, int64_t n, const double *sc, int d
 int p2p_allgather_rows(fcvm_ctx *c, double *v, int64_t n, int64_t row0, int64_t row1, const double *sc, int done_slot) {
   P2PState *s = c->p2p;
   FCVM_CHECK(n <= s->d.slot_n, FCVM_E_ARG, "p2p exchange: %lld doubles exceed the slot size %lld", (long long)n, (long long)s->d.slot_n);
-  k_xchg<1><<<1, XT, 0, c->stream>>>(s->d, v, n, row0, row1, v, sc, done_slot);
+  ProfScope ps(c, 7);
+  k_xchg<1><<<1, XT, 0, c->stream>>>(s->d, ++s->epoch[0], v, n, row0, row1, v, sc, done_slot);
   c->launches++;
   FCVM_CUDA(cudaGetLastError());
   return FCVM_OK;
 }
 
 int p2p_halo(fcvm_ctx *c, double *v, double *sc, int gamma_slot, int rr_slot, bool with_scalars, bool done_check) {
-  k_xchg_halo<<<1, XT, 0, c->stream>>>(c->p2p->d, v, sc, gamma_slot, rr_slot, with_scalars ? 1 : 0, done_check ? 1 : 0);
+  P2PState *s = c->p2p;
+  // every block must be resident while it waits for the peers: far fewer blocks than SMs
+  const int64_t work = 3 * std::max<int64_t>(s->n_send, s->d.n_if);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(48, (work + 4 * HT - 1) / (4 * HT)));
+  ProfScope ps(c, 7);
+  k_xchg_halo<<<grid, HT, 0, c->stream>>>(s->d, ++s->epoch[1], v, sc, gamma_slot, rr_slot, with_scalars ? 1 : 0, done_check ? 1 : 0);
   c->launches++;
   FCVM_CUDA(cudaGetLastError());
   return FCVM_OK;
@@ -262,8 +278,8 @@ extern "C" int fcvm_p2p_create(fcvm_ctx *c, int64_t n_recv_nodes, int64_t slot_n
   d.slot_n = (slot_n + 15) / 16 * 16;
   d.halo_cap = std::max<int64_t>(n_recv_nodes, 1);
   d.off_flags = 0;
-  d.off_epoch = 2 * P2P_MAX_RANKS * 8;
-  d.off_status = d.off_epoch + 16;
+  d.off_ticket = 2 * P2P_MAX_RANKS * 8;
+  d.off_status = d.off_ticket + 16;
   d.off_scal = 256;
   d.off_slots = 1024;
   d.off_halo = d.off_slots + sizeof(double) * 2 * (size_t)d.world * (size_t)d.slot_n;
@@ -304,6 +320,7 @@ extern "C" int fcvm_p2p_attach(fcvm_ctx *c, const void *handles, int npeers, con
   }
   d.npeers = npeers;
   d.n_if = n_if;
+  s->n_send = send_ptr ? send_ptr[npeers] : 0;
   FCVM_TRY(upload(&s->peer_rank, peer_rank, npeers));
   FCVM_TRY(upload(&s->send_ptr, send_ptr, npeers + 1));
   FCVM_TRY(upload(&s->send_node, send_node, send_ptr ? send_ptr[npeers] : 0));

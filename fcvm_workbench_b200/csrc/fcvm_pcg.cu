@@ -429,6 +429,7 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
     for (; it < batch_end; it++) {
       {
         ProfScope ps(c, 3);
+        ProfScope ps11(c, 11);
         const int nxt = (it + 1) & 1;
         // deflated: the vector step's own r.u is void (slot L_RU as a sink), gamma comes with the product
         Slots<2> sl = multi ? Slots<2>{{L_RU, L_RR}} : Slots<2>{{defl ? L_RU : S_GAMMA + nxt, S_RR + nxt}};

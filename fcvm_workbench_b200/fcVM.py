@@ -431,7 +431,8 @@ class Engine:
 
     def profile_get(self):
         """family -> (summed ms of timed launches, timed launches, all launches)."""
-        names = ("spmv", "stress_update", "node_gather", "pcg_vector", "assembly", "elem_stiffness", "coo_reduce")
+        names = ("spmv", "stress_update", "node_gather", "pcg_vector", "assembly", "elem_stiffness", "coo_reduce",
+                 "peer_exchange", "coarse_rhs", "coarse_product", "coarse_expand", "pcg_step")
         out = {}
         for i, k in enumerate(names):
             ms = ctypes.c_double()

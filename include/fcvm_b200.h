@@ -225,7 +225,8 @@ int fcvm_timer_start(fcvm_ctx *ctx);
 int fcvm_timer_stop_ms(fcvm_ctx *ctx, float *ms);
 /* Device time per kernel family, measured with CUDA events on the launching stream;
  * which: 0 = spmv, 1 = stress update, 2 = node gather, 3 = pcg vector kernels, 4 = assembly (whole call),
- * 5 = element stiffness, 6 = COO->SELL reduction.
+ * 5 = element stiffness, 6 = COO->SELL reduction, 7 = peer-memory exchanges of the multi-GPU PCG iteration,
+ * 8 / 9 / 10 = coarse right-hand side / coarse product / expansion of the deflation level, 11 = the vector step (8-11 are also part of 3).
  * on = 0 off; 1 = every launch, synchronising after each (exact, slows the run);
  * on >= 2 = every on-th launch of a family, asynchronously (event pairs from a pool, resolved
  * when read): the timed region keeps running undisturbed.
