@@ -179,6 +179,8 @@ struct fcvm_ctx {
   double *item_part = nullptr;  // [n_items][6]
   float *kz32 = nullptr;        // [18][nent]
   float *einv32 = nullptr;      // [6 ncl][6 ncl]
+  double *rhs_part = nullptr;   // [RHS_SPLIT][6 ncl] shares of the coarse right-hand side
+  int64_t col0 = 0, col1 = 0;   // columns of E^-1 this rank's right-hand side can be non-zero in
   double *lam4 = nullptr;       // [4][6 ncl] column-quarter partials of E^-1 rhs
   int32_t *wk_slice = nullptr;  // [workers + 1] slice range of every SpMV worker
   int wk_grid = 0, wk_split = 0;

@@ -138,6 +138,11 @@ __global__ void k_mirror(int64_t n, const double *__restrict__ L, double *__rest
 }
 
 // rhs_c = sum_{i in c} w_i Z_i^T r_i  -  sum_{(i,t) -> c} (K Z)_(i,t)^T y_i        (one block per cluster)
+// RHS_SPLIT blocks per box, each a fixed share of the box's node list and entry list: with one block per box the
+// time of a box (its 1331 nodes and ~4500 entries walked by 256 threads) is a floor that does not shrink when a
+// rank holds only a few boxes.  The block that finishes last adds the shares in order (loads unrolled: no chain
+// of dependent trips) and publishes the right-hand side.
+constexpr int RHS_SPLIT = 4;          // most; one GPU with all boxes runs one block per box (measured faster there)
 template <typename CT>
 __global__ void __launch_bounds__(256)
 k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restrict__ cl_nodes,
@@ -145,11 +150,13 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
              int64_t nent,
              const double *__restrict__ xyz, const double *__restrict__ fixdof, const double *__restrict__ wt,
              const double *__restrict__ r, const double *__restrict__ y, double *__restrict__ rhs,
-             const double *__restrict__ sc, int done_slot) {
+             double *rhs_part, unsigned int *ticket, int split, const double *__restrict__ sc, int done_slot) {
   if (sc && sc[done_slot] >= 0.0) return;
-  const int c = blockIdx.x;
+  const int c = blockIdx.x / split, share = blockIdx.x % split;
   double v[6] = {0, 0, 0, 0, 0, 0};
-  for (int32_t idx = cl_ptr[c] + threadIdx.x; idx < cl_ptr[c + 1]; idx += 256) {
+  const int32_t nb = cl_ptr[c], nlen = cl_ptr[c + 1] - nb;
+  const int32_t n0 = nb + (int32_t)((int64_t)nlen * share / split), n1 = nb + (int32_t)((int64_t)nlen * (share + 1) / split);
+  for (int32_t idx = n0 + threadIdx.x; idx < n1; idx += 256) {
     const int64_t i = cl_nodes[idx];
     double Z[3][6];
     z_of(g, c, xyz, fixdof, i, Z);
@@ -161,8 +168,9 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
   if (y) {
     // entries of this box: consecutive lanes read consecutive doubles of each of the 18 component planes
     // two entries per trip: the dependent chains (entry -> node -> y) of both are in flight together
-    const int32_t e1 = ent_ptr[c + 1];
-    int32_t idx = ent_ptr[c] + threadIdx.x;
+    const int32_t eb = ent_ptr[c], elen = ent_ptr[c + 1] - eb;
+    const int32_t e1 = eb + (int32_t)((int64_t)elen * (share + 1) / split);
+    int32_t idx = eb + (int32_t)((int64_t)elen * share / split) + threadIdx.x;
     for (; idx + 256 < e1; idx += 512) {
       const int64_t i = ent_node[idx], j = ent_node[idx + 256];
       const CT *kz = kzs + idx;
@@ -198,28 +206,53 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
     if (lane == 0) sm[m][warp] = s;
   }
   __syncthreads();
+  const int64_t n6 = 6 * (int64_t)(gridDim.x / split);
   if (threadIdx.x < 6) {
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; w++) s += sm[threadIdx.x][w];
-    rhs[6 * (int64_t)c + threadIdx.x] = s;
+    (split == 1 ? rhs : rhs_part + (int64_t)share * n6)[6 * (int64_t)c + threadIdx.x] = s;
+  }
+  if (split == 1) return;
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    for (int64_t q0 = threadIdx.x; q0 < n6; q0 += 4 * 256) {
+      double p[4][RHS_SPLIT];
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int k = 0; k < RHS_SPLIT; k++)
+          p[t][k] = (k < split && q0 + 256 * t < n6) ? __ldcg(rhs_part + k * n6 + q0 + 256 * t) : 0.0;
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+        if (q0 + 256 * t < n6) rhs[q0 + 256 * t] = ((p[t][0] + p[t][1]) + p[t][2]) + p[t][3];
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
   }
 }
 
-// lam = Einv rhs for rows [row0, row1): four warps per row (a quarter of the columns each, four loads in flight
-// per lane), partial sums added in warp order -- one warp per row left every warp with 48 dependent trips to HBM
+// y = Einv[:, col0:col1) x[col0:col1) for all n rows: four warps per row (a quarter of the column range each, four
+// loads in flight per lane), partial sums added in warp order.  On one GPU the range is everything; on a
+// partitioned mesh a rank's right-hand side is non-zero only for the boxes around its own nodes, so it multiplies
+// just that column panel and the ranks' products are summed (linearity) -- one exchange instead of two.
 template <typename CT>
 __global__ void __launch_bounds__(256)
-k_gemv(int64_t n, int64_t row0, int64_t row1, const CT *__restrict__ A, const double *__restrict__ x,
+k_gemv(int64_t n, int64_t col0, int64_t col1, const CT *__restrict__ A, const double *__restrict__ x,
        double *__restrict__ y, const double *__restrict__ sc, int done_slot) {
   if (sc && sc[done_slot] >= 0.0) return;
   __shared__ double part[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, quarter = warp & 3;
-  const int64_t row = row0 + blockIdx.x * 2 + (warp >> 2);
+  const int64_t row = blockIdx.x * 2 + (warp >> 2);
   double s = 0.0;
-  if (row < row1) {
+  if (row < n) {
     const CT *a = A + row * n;
-    const int64_t c0 = quarter * n / 4, c1 = (quarter + 1) * n / 4;
+    const int64_t w = col1 - col0, c0 = col0 + quarter * w / 4, c1 = col0 + (quarter + 1) * w / 4;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int64_t q = c0 + lane;
     for (; q + 96 < c1; q += 128) {
@@ -233,7 +266,7 @@ k_gemv(int64_t n, int64_t row0, int64_t row1, const CT *__restrict__ A, const do
   }
   if (lane == 0) part[warp] = s;
   __syncthreads();
-  if (row < row1 && quarter == 0 && lane == 0) y[row] = ((part[warp] + part[warp + 1]) + part[warp + 2]) + part[warp + 3];
+  if (row < n && quarter == 0 && lane == 0) y[row] = ((part[warp] + part[warp + 1]) + part[warp + 2]) + part[warp + 3];
 }
 
 // out_i = (base ? base_i : 0) + Z_i lam_(cluster of i)
@@ -306,6 +339,19 @@ extern "C" int fcvm_set_deflation(fcvm_ctx *c, int ncx, int ncy, int ncz, const 
   FCVM_TRY(dalloc2(&c->kz_rel, 8 * nn));
   FCVM_TRY(dalloc2(&c->dE, 36 * ncl * ncl)); FCVM_TRY(dalloc2(&c->dEinv, 36 * ncl * ncl));
   FCVM_TRY(dalloc2(&c->d_rhs, 6 * ncl)); FCVM_TRY(dalloc2(&c->d_lam, 6 * ncl));
+  FCVM_TRY(dalloc2(&c->rhs_part, RHS_SPLIT * 6 * ncl));
+  {
+    // Boxes this rank's right-hand side can touch: the boxes of its nodes and their neighbours -- a contiguous
+    // range of box numbers that covers them.  The coarse product of a rank only needs those columns of E^-1.
+    int64_t lo_c = ncl, hi_c = -1;
+    for (int64_t i = 0; i < nn; i++) {
+      lo_c = std::min<int64_t>(lo_c, cid[i]);
+      hi_c = std::max<int64_t>(hi_c, cid[i]);
+    }
+    const int64_t reach = 1 + ncx + (int64_t)ncx * ncy;
+    c->col0 = 6 * std::max<int64_t>(0, lo_c - reach);
+    c->col1 = 6 * (std::min<int64_t>(ncl - 1, hi_c + reach) + 1);
+  }
   FCVM_TRY(dalloc2(&c->spmv_part2, c->nslices + 8));
   FCVM_CUDA(cudaMemset(c->spmv_part2, 0, sizeof(double) * (c->nslices + 8)));
   return FCVM_OK;
@@ -319,7 +365,6 @@ void fused_free(fcvm_ctx *c);
 bool coarse_fp32();
 bool p2p_ready(const fcvm_ctx *c);
 int p2p_allreduce_sum(fcvm_ctx *c, double *v, int64_t n, const double *sc, int done_slot);
-int p2p_allgather_rows(fcvm_ctx *c, double *v, int64_t n, int64_t row0, int64_t row1, const double *sc, int done_slot);
 
 // K Z, E = Z^T K Z and its inverse for the matrix now in the context (called at the end of fcvm_assemble)
 int deflation_build(fcvm_ctx *c) {
@@ -443,41 +488,33 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
   const bool f32 = coarse_fp32() && c->kz32 && c->einv32;
   {
   ProfScope ps8(c, 8);
+  const int split = c->world > 1 ? RHS_SPLIT : 1;
   if (f32)
-    k_coarse_rhs<float><<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz32, c->nent, c->xyz,
-                                                         fixdof, c->dof_weight, r, y, c->d_rhs, sc, done_slot);
+    k_coarse_rhs<float><<<(unsigned)(split * c->ncl), 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz32,
+                                                                   c->nent, c->xyz, fixdof, c->dof_weight, r, y, c->d_rhs,
+                                                                   c->rhs_part, c->red_counter + 3, split, sc, done_slot);
   else
-    k_coarse_rhs<double><<<(unsigned)c->ncl, 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val, c->nent,
-                                                          c->xyz, fixdof, c->dof_weight, r, y, c->d_rhs, sc, done_slot);
+    k_coarse_rhs<double><<<(unsigned)(split * c->ncl), 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val,
+                                                                    c->nent, c->xyz, fixdof, c->dof_weight, r, y, c->d_rhs,
+                                                                    c->rhs_part, c->red_counter + 3, split, sc, done_slot);
+  }
+  {
+    // every rank holds E^-1 and multiplies the column panel its own right-hand side lives in (all columns on one GPU)
+    const bool multi = c->world > 1;
+    const int64_t col0 = multi ? c->col0 : 0, col1 = multi ? c->col1 : n6;
+    ProfScope ps9(c, 9);
+    if (f32)
+      k_gemv<float><<<grid_for(n6, 2), 256, 0, st>>>(n6, col0, col1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
+    else
+      k_gemv<double><<<grid_for(n6, 2), 256, 0, st>>>(n6, col0, col1, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
   }
   if (c->world > 1) {
-    // every rank holds E^-1 and applies its own share of the rows.  Inside one box the two collectives are
-    // peer-memory exchanges (fcvm_p2p.cu: sums in rank order, identical on all ranks); without mapped arenas
-    // NCCL all-reduces (the row shares put together over a vector that is zero elsewhere: x + 0 = x, exact)
-    const bool p2p = p2p_ready(c);
-    if (p2p)
-      FCVM_TRY(p2p_allreduce_sum(c, c->d_rhs, n6, sc, done_slot));
-    else
-      FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_rhs, n6));
-    const int64_t row0 = n6 * c->rank / c->world, row1 = n6 * (c->rank + 1) / c->world;
-    if (!p2p) FCVM_CUDA(cudaMemsetAsync(c->d_lam, 0, sizeof(double) * n6, st));
-    {
-      ProfScope ps9(c, 9);
-      if (f32)
-        k_gemv<float><<<grid_for(row1 - row0, 2), 256, 0, st>>>(n6, row0, row1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
-      else
-        k_gemv<double><<<grid_for(row1 - row0, 2), 256, 0, st>>>(n6, row0, row1, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
-    }
-    if (p2p)
-      FCVM_TRY(p2p_allgather_rows(c, c->d_lam, n6, row0, row1, sc, done_slot));
+    // lam = sum over ranks of their products: inside one box a peer-memory exchange (fcvm_p2p.cu: sums in rank
+    // order, identical on all ranks), else an NCCL all-reduce
+    if (p2p_ready(c))
+      FCVM_TRY(p2p_allreduce_sum(c, c->d_lam, n6, sc, done_slot));
     else
       FCVM_TRY(fcvm_comm_allreduce_sum(c, c->d_lam, n6));
-  } else if (f32) {
-    ProfScope ps9(c, 9);
-    k_gemv<float><<<grid_for(n6, 2), 256, 0, st>>>(n6, 0, n6, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
-  } else {
-    ProfScope ps9(c, 9);
-    k_gemv<double><<<grid_for(n6, 2), 256, 0, st>>>(n6, 0, n6, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
   }
   ProfScope ps10(c, 10);
   k_expand<<<grid_for(c->nn, 256), 256, 0, st>>>(c->nn, g, c->d_cid, c->xyz, fixdof, c->d_lam, base, out, sc, done_slot);
@@ -491,7 +528,8 @@ void deflation_free(fcvm_ctx *c) {
   cudaFree(c->cl_active); c->cl_active = nullptr;
   cudaFree(c->d_cid); cudaFree(c->cl_ptr); cudaFree(c->cl_nodes); cudaFree(c->kz_rel); cudaFree(c->kz_val);
   cudaFree(c->ent_ptr); cudaFree(c->ent); cudaFree(c->ent_inv); c->ent_inv = nullptr; cudaFree(c->dE); cudaFree(c->dEinv); cudaFree(c->d_rhs); cudaFree(c->d_lam);
-  cudaFree(c->spmv_part2);
+  cudaFree(c->spmv_part2); cudaFree(c->rhs_part);
+  c->rhs_part = nullptr;
   c->d_cid = c->cl_ptr = c->cl_nodes = c->ent_ptr = c->ent = nullptr;
   c->kz_rel = nullptr;
   c->kz_val = c->dE = c->dEinv = c->d_rhs = c->d_lam = c->spmv_part2 = nullptr;

@@ -5,11 +5,11 @@
 // (st.global on mapped peer pointers), (2) publishes an epoch flag with release semantics at system scope,
 // (3) spins on its own flags until every contributor's epoch has arrived (acquire), and (4) combines the
 // contributions in ascending rank order -- so every rank computes bit-identical sums and takes the same
-// decisions.  Three exchanges per PCG iteration replace four NCCL all-reduces (and their launch latency, which
+// decisions.  Two exchanges per PCG iteration replace four NCCL all-reduces (and their launch latency, which
 // dominated the iteration at 8 GPUs):
 //
-//   k_xchg<SUM>     right-hand side of the coarse problem (6 x boxes doubles from every rank)
-//   k_xchg<GATHER>  coarse solution, each rank contributes the rows it multiplied
+//   k_xchg_sum      coarse solution: every rank multiplies the column panel of E^-1 its own right-hand side lives
+//                   in, the products (6 x boxes doubles per rank) are summed
 //   k_xchg_halo     rows of w = K u at shared nodes -- neighbours only (Partition.p2p_plan), not a dense global
 //                   interface vector -- together with the three per-rank scalars of the iteration
 //
@@ -17,7 +17,7 @@
 // can never overwrite data that is still being read: to be two exchanges ahead it would need this rank's flag
 // of the exchange in between.  (The no-op launches after convergence are skipped by all ranks together -- the
 // flag they test is itself a bit-identical sum -- and the next real exchange follows a host synchronisation.)
-// A rank that waits longer than ~20 s raises a status flag instead of hanging.  NCCL stays for everything outside
+// A rank that waits longer than ~6 s raises a status flag instead of hanging.  NCCL stays for everything outside
 // the iteration.
 #include <algorithm>
 
@@ -66,7 +66,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-constexpr long long SPIN_LIMIT = 40000000000LL;    // SM cycles (~20 s)
+constexpr long long SPIN_LIMIT = 12000000000LL;    // SM cycles (~6 s)
 constexpr int XT = 1024;
 
 // publish epoch e on channel ch to every rank (the block whose `publish` is set), then wait for everyone's
@@ -94,38 +94,27 @@ __device__ __forceinline__ bool signal_and_wait(const P2PDev &d, int ch, unsigne
   return true;
 }
 
-// MODE 0: out[i] = sum over ranks of their src[i], i < n (ascending rank)
-// MODE 1: every rank contributes src[seg0..seg1); out[0..n) = the assembled vector
-template <int MODE>
+// out[i] = sum over ranks of their src[i], i < n (ascending rank)
 __global__ void __launch_bounds__(XT)
-k_xchg(P2PDev d, unsigned long long e, const double *src, long long n, long long seg0, long long seg1, double *out,
-       const double *sc, int done_slot) {
+k_xchg_sum(P2PDev d, unsigned long long e, const double *src, long long n, double *out, const double *sc, int done_slot) {
   if (sc && sc[done_slot] >= 0.0) return;            // every rank holds the same flag
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;
   const long long par = (long long)(e & 1ull);
   for (int p = 0; p < d.world; p++) {
-    double *slots = (double *)(d.peer[p] + d.off_slots);
-    if (MODE == 0) {
-      double *dst = slots + (par * d.world + d.rank) * d.slot_n;
-      for (long long i = threadIdx.x; i < n; i += XT) dst[i] = src[i];
-    } else {
-      double *dst = slots + par * d.world * d.slot_n;
-      for (long long i = seg0 + threadIdx.x; i < seg1; i += XT) dst[i] = src[i];
-    }
+    double *dst = (double *)(d.peer[p] + d.off_slots) + (par * d.world + d.rank) * d.slot_n;
+    for (long long i = threadIdx.x; i < n; i += XT) dst[i] = src[i];
   }
-  __threadfence_system();
+  // release pattern: the block's stores happen before the barrier, the flag writers fence at system scope after it
+  // (fences are cumulative) -- one fence per flag writer instead of one per thread
   __syncthreads();
+  if ((int)threadIdx.x < d.world) __threadfence_system();
   if (!signal_and_wait(d, 0, e, true, &bad)) return;
   const double *mine = (const double *)(d.peer[d.rank] + d.off_slots) + par * d.world * d.slot_n;
   for (long long i = threadIdx.x; i < n; i += XT) {
-    if (MODE == 0) {
-      double s = 0.0;
-      for (int r = 0; r < d.world; r++) s += __ldcg(mine + r * d.slot_n + i);
-      out[i] = s;
-    } else {
-      out[i] = __ldcg(mine + i);
-    }
+    double s = 0.0;
+    for (int r = 0; r < d.world; r++) s += __ldcg(mine + r * d.slot_n + i);
+    out[i] = s;
   }
 }
 
@@ -155,17 +144,15 @@ k_xchg_halo(P2PDev d, unsigned long long e, double *v, double *sc, int gamma_slo
     const double val = sc[threadIdx.x == 0 ? L_RU : (threadIdx.x == 1 ? L_RR : L_WU)];
     for (int p = 0; p < d.world; p++) ((double *)(d.peer[p] + d.off_scal))[(par * P2P_MAX_RANKS + d.rank) * 4 + threadIdx.x] = val;
   }
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();        // this block's pushes (ordered before the barrier) before its ticket
     unsigned int *ticket = (unsigned int *)(d.peer[d.rank] + d.off_ticket);
     publish = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-    if (publish) {
-      *ticket = 0u;
-      __threadfence_system();      // the other blocks' pushes (observed through the ticket) before the flags
-    }
+    if (publish) *ticket = 0u;
   }
   __syncthreads();
+  if (publish && (int)threadIdx.x < d.world) __threadfence_system();   // the other blocks' pushes (seen through the ticket) before the flags
   // the scalars go to every rank, the rows to the neighbours only: one flag round over all ranks covers both
   if (!signal_and_wait(d, 1, e, publish != 0, &bad)) return;
   const double *halo = (const double *)(d.peer[d.rank] + d.off_halo) + 3 * par * d.halo_cap;
@@ -209,17 +196,7 @@ int p2p_allreduce_sum(fcvm_ctx *c, double *v, int64_t n, const double *sc, int d
   P2PState *s = c->p2p;
   FCVM_CHECK(n <= s->d.slot_n, FCVM_E_ARG, "p2p exchange: %lld doubles exceed the slot size %lld", (long long)n, (long long)s->d.slot_n);
   ProfScope ps(c, 7);
-  k_xchg<0><<<1, XT, 0, c->stream>>>(s->d, ++s->epoch[0], v, n, 0, 0, v, sc, done_slot);
-  c->launches++;
-  FCVM_CUDA(cudaGetLastError());
-  return FCVM_OK;
-}
-
-int p2p_allgather_rows(fcvm_ctx *c, double *v, int64_t n, int64_t row0, int64_t row1, const double *sc, int done_slot) {
-  P2PState *s = c->p2p;
-  FCVM_CHECK(n <= s->d.slot_n, FCVM_E_ARG, "p2p exchange: %lld doubles exceed the slot size %lld", (long long)n, (long long)s->d.slot_n);
-  ProfScope ps(c, 7);
-  k_xchg<1><<<1, XT, 0, c->stream>>>(s->d, ++s->epoch[0], v, n, row0, row1, v, sc, done_slot);
+  k_xchg_sum<<<1, XT, 0, c->stream>>>(s->d, ++s->epoch[0], v, n, v, sc, done_slot);
   c->launches++;
   FCVM_CUDA(cudaGetLastError());
   return FCVM_OK;

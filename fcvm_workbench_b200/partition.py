@@ -264,10 +264,13 @@ class Comm:
         i32p = ctypes.POINTER(ctypes.c_int32)
         ok = os.environ.get("FCVM_P2P", "1") != "0" and self.world <= 8
         plan = self.part.p2p_plan(self.rank) if ok else None
+        # every arena has the same layout: a sender computes addresses inside its PEER's arena, so the capacity of
+        # the receive area (it sets the offset of the second buffer) must not depend on the rank
+        halo_cap = max(self.allgather(plan["n_recv"] if ok else 0))
         handle = (ctypes.c_ubyte * 64)()
         if ok:
             try:
-                call("fcvm_p2p_create", eng._ctx, plan["n_recv"], self.P2P_SLOT, ctypes.cast(handle, ctypes.c_void_p))
+                call("fcvm_p2p_create", eng._ctx, halo_cap, self.P2P_SLOT, ctypes.cast(handle, ctypes.c_void_p))
             except FcvmError:
                 ok = False
         every = self.allgather((ok, bytes(handle)))

@@ -176,25 +176,31 @@ def test_p2p_plan_reproduces_the_global_interface_sum(world):
     total = np.zeros((m.nn, 3))
     for r in range(world):
         total[part.nodes[r]] += local[r]
-    recv = [np.full((p["n_recv"], 3), np.nan) for p in plans]
-    for r, p in enumerate(plans):
-        assert list(p["peers"]) == sorted(set(p["peers"])) and r not in p["peers"]
-        for k, q in enumerate(p["peers"]):
-            nodes = p["send_node"][p["send_ptr"][k]:p["send_ptr"][k + 1]]
-            assert (np.diff(part.nodes[r][nodes]) > 0).all()                   # ascending global id
-            off = int(p["remote_off"][k])
-            recv[q][off:off + nodes.size] = local[r][nodes]
-    out = []
-    for r, p in enumerate(plans):
-        v = local[r].copy()
-        for i, node in enumerate(p["if_node"]):
-            s = np.zeros(3)
-            for src in p["if_src"][p["if_ptr"][i]:p["if_ptr"][i + 1]]:
-                s = s + (local[r][node] if src < 0 else recv[r][src])
-            v[node] = s
-        assert not np.isnan(v).any()
-        out.append(v)
-        np.testing.assert_allclose(v, total[part.nodes[r]], rtol=0, atol=1e-13)
+    # the arenas as the kernel addresses them (csrc/fcvm_p2p.cu): two receive buffers of ONE capacity for all ranks,
+    # a sender writes at 3 * (parity * cap + remote_off + k) inside its PEER's arena
+    cap = max(p["n_recv"] for p in plans)
+    for parity in (0, 1):
+        arena = [np.full((2 * cap, 3), np.nan) for _ in range(world)]
+        for r, p in enumerate(plans):
+            assert list(p["peers"]) == sorted(set(p["peers"])) and r not in p["peers"]
+            for k, q in enumerate(p["peers"]):
+                nodes = p["send_node"][p["send_ptr"][k]:p["send_ptr"][k + 1]]
+                assert (np.diff(part.nodes[r][nodes]) > 0).all()                   # ascending global id
+                off = parity * cap + int(p["remote_off"][k])
+                assert np.isnan(arena[q][off:off + nodes.size]).all()              # segments do not overlap
+                arena[q][off:off + nodes.size] = local[r][nodes]
+        out = []
+        for r, p in enumerate(plans):
+            v = local[r].copy()
+            halo = arena[r][parity * cap:(parity + 1) * cap]
+            for i, node in enumerate(p["if_node"]):
+                s = np.zeros(3)
+                for src in p["if_src"][p["if_ptr"][i]:p["if_ptr"][i + 1]]:
+                    s = s + (local[r][node] if src < 0 else halo[src])
+                v[node] = s
+            assert not np.isnan(v).any()
+            out.append(v)
+            np.testing.assert_allclose(v, total[part.nodes[r]], rtol=0, atol=1e-13)
     glob = {}
     for r in range(world):                                                      # bit-identical across holders
         for gid, row in zip(part.nodes[r], out[r]):
