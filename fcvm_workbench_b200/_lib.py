@@ -37,6 +37,9 @@ _SIGNATURES = {
     "fcvm_synchronize": [ctxp],
     "fcvm_set_mesh": [ctxp, c_int64, c_int64, i64p, f64p, c_double, c_double, c_double],
     "fcvm_set_constraints": [ctxp, u8p, f64p],
+    "fcvm_set_coordinates": [ctxp, f64p],
+    "fcvm_assemble_buckling": [ctxp, c_double],
+    "fcvm_spmv_geometric": [ctxp, c_void_p, c_void_p],
     "fcvm_set_interface": [ctxp, f64p, c_int64, i64p, i64p, c_int64],
     "fcvm_vec_alloc": [ctxp, c_int64, POINTER(c_void_p)],
     "fcvm_vec_free": [ctxp, c_void_p],

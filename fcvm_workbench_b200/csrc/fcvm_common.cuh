@@ -107,6 +107,7 @@ struct fcvm_ctx {
   int32_t *node_slot = nullptr; // [nn]
   int32_t *colidx = nullptr;    // [nblk_stored] block column (node)
   double *vals = nullptr;       // [nblk_stored/32][9][32]
+  double *vals2 = nullptr;      // same layout: geometric stiffness G of the linear buckling analysis
   uint32_t *blk_first = nullptr;// [nblk_stored] first contribution in src
   uint32_t *blk_cnt = nullptr;  // [nblk_stored] number of contributions (0 for padding)
   uint32_t *src = nullptr;      // [100*ne] ((pair*ne + e) << 1) | transpose
@@ -181,6 +182,7 @@ struct fcvm_ctx {
   float *einv32 = nullptr;      // [6 ncl][6 ncl]
   double *rhs_part = nullptr;   // [RHS_SPLIT][6 ncl] shares of the coarse right-hand side
   int64_t col0 = 0, col1 = 0;   // columns of E^-1 this rank's right-hand side can be non-zero in
+  int64_t local_boxes = 0;      // boxes that hold nodes of this rank
   double *lam4 = nullptr;       // [4][6 ncl] column-quarter partials of E^-1 rhs
   int32_t *wk_slice = nullptr;  // [workers + 1] slice range of every SpMV worker
   int wk_grid = 0, wk_split = 0;

@@ -323,7 +323,7 @@ static void free_mesh(fcvm_ctx *c) {
     if (c->buf[i]) cudaFree(c->buf[i]);
     c->buf[i] = nullptr;
   }
-  dfree(c->slice_ptr); dfree(c->slot_node); dfree(c->node_slot); dfree(c->colidx); dfree(c->vals);
+  dfree(c->slice_ptr); dfree(c->slot_node); dfree(c->node_slot); dfree(c->colidx); dfree(c->vals); dfree(c->vals2);
   dfree(c->blk_first); dfree(c->blk_cnt); dfree(c->src); dfree(c->diag_pos); dfree(c->row_first);
   dfree(c->row_cols); dfree(c->cooK); dfree(c->minv);
   dfree(c->pcg_r); dfree(c->pcg_z); dfree(c->pcg_p); dfree(c->pcg_q); dfree(c->pcg_s); dfree(c->spmv_part);
@@ -606,6 +606,19 @@ extern "C" int fcvm_set_constraints(fcvm_ctx *c, const uint8_t *fixmask, const d
   c->defl_structure = false;
   c->defl_ready = false;
   return FCVM_OK;
+}
+
+// New nodal coordinates on the same mesh topology (the imperfect geometry of fcVM.py:1240): the sparsity pattern
+// and all index structures stay, the geometry-dependent data is recomputed, the matrix must be assembled again.
+extern "C" int fcvm_set_coordinates(fcvm_ctx *c, const double *nocoord) {
+  FCVM_CHECK(c && c->nn > 0 && nocoord, FCVM_E_ARG, "fcvm_set_coordinates: call fcvm_set_mesh first");
+  FCVM_CUDA(cudaMemcpyAsync(c->xyz, nocoord, sizeof(double) * 3 * c->nn, cudaMemcpyHostToDevice, c->stream));
+  FCVM_CUDA(cudaStreamSynchronize(c->stream));
+  c->assembled = false;
+  c->matrix_elastic = false;
+  c->defl_ready = c->defl_structure = false;
+  dfree(c->egeo); dfree(c->tile_affine);
+  return matfree_set_mesh(c);
 }
 
 extern "C" int fcvm_set_interface(fcvm_ctx *c, const double *dof_weight, int64_t n_if_local,

@@ -348,6 +348,8 @@ extern "C" int fcvm_set_deflation(fcvm_ctx *c, int ncx, int ncy, int ncz, const 
       lo_c = std::min<int64_t>(lo_c, cid[i]);
       hi_c = std::max<int64_t>(hi_c, cid[i]);
     }
+    c->local_boxes = 0;
+    for (int64_t k = 0; k < ncl; k++) c->local_boxes += ptr[(size_t)k + 1] > ptr[(size_t)k] ? 1 : 0;
     const int64_t reach = 1 + ncx + (int64_t)ncx * ncy;
     c->col0 = 6 * std::max<int64_t>(0, lo_c - reach);
     c->col1 = 6 * (std::min<int64_t>(ncl - 1, hi_c + reach) + 1);
@@ -488,7 +490,8 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
   const bool f32 = coarse_fp32() && c->kz32 && c->einv32;
   {
   ProfScope ps8(c, 8);
-  const int split = c->world > 1 ? RHS_SPLIT : 1;
+  // several blocks per box only when this rank holds too few boxes to fill the GPU with one block each
+  const int split = c->local_boxes < 800 ? RHS_SPLIT : 1;
   if (f32)
     k_coarse_rhs<float><<<(unsigned)(split * c->ncl), 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz32,
                                                                    c->nent, c->xyz, fixdof, c->dof_weight, r, y, c->d_rhs,

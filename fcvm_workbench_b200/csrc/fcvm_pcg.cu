@@ -248,15 +248,23 @@ __global__ void k_tail_get(const double *__restrict__ tail, double *sc, int gamm
 
 static void spmv_launch(fcvm_ctx *c, const double *x, double *y, const double *sc, int rr_slot, double *dot_part,
                         const int32_t *list = nullptr, int64_t nlist = -1, const double *rvec = nullptr,
-                        double *dot_part2 = nullptr) {
+                        double *dot_part2 = nullptr, const double *vals = nullptr) {
   const int64_t nb = list ? nlist : c->nslices;
   if (nb <= 0) return;
   k_spmv_sell<<<(unsigned)nb, 32 * SPMV_SPLIT, 0, c->stream>>>(nb, list, c->slice_ptr, c->slot_node, c->colidx,
-                                                              c->vals, x, y, sc, rr_slot, dot_part, rvec,
+                                                              vals ? vals : c->vals, x, y, sc, rr_slot, dot_part, rvec,
                                                               c->dof_weight, dot_part2);
 }
 
 namespace fcvm {
+// the same product with another value array on the context's pattern (geometric stiffness)
+int launch_spmv_values(fcvm_ctx *c, const double *vals, const double *x, double *y) {
+  ProfScope ps(c, 0);
+  spmv_launch(c, x, y, nullptr, 0, nullptr, nullptr, -1, nullptr, nullptr, vals);
+  c->launches++;
+  FCVM_CUDA(cudaGetLastError());
+  return FCVM_OK;
+}
 int launch_spmv(fcvm_ctx *c, const double *x, double *y) {
   ProfScope ps(c, 0);
   spmv_launch(c, x, y, nullptr, 0, nullptr);

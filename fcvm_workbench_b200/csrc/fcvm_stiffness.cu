@@ -25,10 +25,20 @@ constexpr int KE_ROW = 35;          // doubles per element of the coordinate sta
 constexpr int KE_PAD = 33;          // row stride of the gradient tiles
 
 struct TangentArgs {
-  const double *sig_old;   // SoA
+  const double *sig_old;   // SoA (tangent: stress at the start of the step; buckling: the elastic stress state)
   const uint8_t *pgp;      // SoA
   double G, H;
+  const uint32_t *emask;   // buckling: prescribed dofs of every element (bit 3k+c)
+  double sigma;            // buckling: shift
 };
+
+// what k_elem_stiffness integrates
+//   KE_ELASTIC     B^T D B                                   calcGSM, fcVM.py:620-816
+//   KE_TANGENT     B^T (D - pmat) B at plastic points        calcTSM nstep > 1, fcVM.py:983-999
+//   KE_BUCKLING_M  K - sigma G of the linear buckling analysis (calcTSM nstep == 1, fcVM.py:1002-1006, 1063-1073):
+//                  K = B^T D B NOT eliminated, diagonal entries of prescribed dofs times 100; G = -nsm
+//   KE_BUCKLING_G  G = -nsm, nsm = GM^T (sigma_ij x I3) GM the geometric stiffness of the stress state
+enum { KE_ELASTIC = 0, KE_TANGENT = 1, KE_BUCKLING_M = 2, KE_BUCKLING_G = 3 };
 
 // rows a of the lower block triangle handled by each warp (a+1 blocks per row): 14, 14, 14, 13 blocks
 __constant__ int c_rows[4][4] = {{9, 3, -1, -1}, {8, 4, -1, -1}, {7, 5, -1, -1}, {6, 2, 1, 0}};
@@ -41,7 +51,7 @@ __constant__ int c_rows[4][4] = {{9, 3, -1, -1}, {8, 4, -1, -1}, {7, 5, -1, -1},
 //   phase B  the 55 blocks K_ab (a >= b) = lambda P + mu P^T + mu tr(P) I (- plastic correction),
 //            P = sum_gp g_a g_b^T, split over the warps by rows of equal work; each block row of 32
 //            elements x 9 entries leaves through a per-warp staging tile as one contiguous 2304-byte run
-template <bool TANGENT>
+template <int MODE>
 __global__ void __launch_bounds__(KE_THREADS, 4)
 k_elem_stiffness(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
                  const double *__restrict__ disp, double lambda, double mu, TangentArgs ta, double gx, double gy,
@@ -49,7 +59,8 @@ k_elem_stiffness(int64_t ne, const int32_t *__restrict__ conn, const double *__r
   __shared__ double sG[4 * 30 * KE_PAD];          // coordinate staging [32][35] first, then gradient tiles [4][30][33]
   __shared__ double sO[4][KE_E * 9];              // per-warp output staging
   __shared__ double sW[4][KE_E];                  // w|J| per Gauss point
-  __shared__ double sS[TANGENT ? 4 * 7 * KE_E : 1];   // [gp][6 deviator comps + factor][element]
+  constexpr bool TANGENT = MODE == KE_TANGENT, GEOM = MODE >= KE_BUCKLING_M;
+  __shared__ double sS[(TANGENT || GEOM) ? 4 * 7 * KE_E : 1];   // [gp][6 deviator (tangent) / stress (buckling) comps + factor][element]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t e0 = (int64_t)blockIdx.x * KE_E;
   const int64_t e = min(e0 + lane, ne - 1);
@@ -109,6 +120,10 @@ k_elem_stiffness(int64_t ne, const int32_t *__restrict__ conn, const double *__r
       for (int c = 0; c < 6; c++) sS[(warp * 7 + c) * KE_E + lane] = sd[c];
       sS[(warp * 7 + 6) * KE_E + lane] = pf;
     }
+    if (GEOM) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) sS[(warp * 7 + c) * KE_E + lane] = ta.sig_old[((int64_t)c * 4 + warp) * ne + e];
+    }
   }
   __syncthreads();
   const bool live = e0 + lane < ne;
@@ -153,6 +168,7 @@ k_elem_stiffness(int64_t ne, const int32_t *__restrict__ conn, const double *__r
     for (int b = 0; b <= a; b++) {
       double P[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
       double Q[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      double sab = 0.0;                  // buckling: sum_gp w grad N_a . sigma grad N_b
 #pragma unroll
       for (int gp = 0; gp < 4; gp++) {
         double gb[3];
@@ -162,6 +178,14 @@ k_elem_stiffness(int64_t ne, const int32_t *__restrict__ conn, const double *__r
         for (int i = 0; i < 3; i++)
 #pragma unroll
           for (int j = 0; j < 3; j++) P[i][j] += ga[gp][i] * gb[j];
+        if (GEOM) {
+          double sg[6];
+#pragma unroll
+          for (int c = 0; c < 6; c++) sg[c] = sS[(gp * 7 + c) * KE_E + lane];
+          sab += ga[gp][0] * (sg[0] * gb[0] + sg[3] * gb[1] + sg[4] * gb[2]) +
+                 ga[gp][1] * (sg[3] * gb[0] + sg[1] * gb[1] + sg[5] * gb[2]) +
+                 ga[gp][2] * (sg[4] * gb[0] + sg[5] * gb[1] + sg[2] * gb[2]);
+        }
         if (TANGENT) {
           const double f = sS[(gp * 7 + 6) * KE_E + lane];
           if (f != 0.0) {
@@ -188,6 +212,11 @@ k_elem_stiffness(int64_t ne, const int32_t *__restrict__ conn, const double *__r
         for (int j = 0; j < 3; j++) {
           double v = lambda * P[i][j] + mu * P[j][i] + (i == j ? tr : 0.0);
           if (TANGENT) v -= Q[i][j];
+          if (MODE == KE_BUCKLING_M) {
+            if (a == b && i == j && ((ta.emask[e] >> (3 * a + i)) & 1u)) v *= 100.0;      // fcVM.py:1071-1072
+            if (i == j) v += ta.sigma * sab;                                              // K - sigma G, G = -nsm
+          }
+          if (MODE == KE_BUCKLING_G) v = (i == j) ? -sab : 0.0;
           so[lane * 9 + 3 * i + j] = v;
         }
       __syncwarp();
@@ -353,7 +382,7 @@ __global__ void k_gather_blocks(int64_t nn, const int32_t *__restrict__ row_firs
 }
 
 int run_elem_stiffness(fcvm_ctx *c, int tangent, const double *disp, double Et_E, bool gravity, double gx,
-                       double gy, double gz) {
+                       double gy, double gz, double sigma = 0.0) {
   const double E = c->E, nu = c->nu;
   const double dm = E * (1.0 - nu) / (1.0 + nu) / (1.0 - 2.0 * nu);
   const double lambda = dm * (nu / (1.0 - nu));
@@ -364,17 +393,26 @@ int run_elem_stiffness(fcvm_ctx *c, int tangent, const double *disp, double Et_E
   ta.G = E / (1.0 + nu) / 2.0;
   if (Et_E > 0.95) Et_E = 0.95;
   ta.H = (Et_E * E) / (1.0 - Et_E);
+  ta.emask = c->emask;
+  ta.sigma = sigma;
+  if (tangent >= KE_BUCKLING_M) ta.sig_old = (const double *)c->buf[FCVM_BUF_SIG_NEW];   // the elastic stress state
   const size_t smem = 0;
   const int grid = grid_for(c->ne, KE_E);
   ProfScope ps(c, 5);
   double *elv = gravity ? c->elv : nullptr;
   const double rho = c->density;
-  if (tangent)
-    k_elem_stiffness<true><<<grid, KE_THREADS, smem, c->stream>>>(c->ne, c->conn, c->xyz, disp, lambda, mu, ta,
-                                                                  gx * rho, gy * rho, gz * rho, c->cooK, elv);
+  if (tangent == KE_TANGENT)
+    k_elem_stiffness<KE_TANGENT><<<grid, KE_THREADS, smem, c->stream>>>(c->ne, c->conn, c->xyz, disp, lambda, mu, ta,
+                                                                        gx * rho, gy * rho, gz * rho, c->cooK, elv);
+  else if (tangent == KE_BUCKLING_M)
+    k_elem_stiffness<KE_BUCKLING_M><<<grid, KE_THREADS, smem, c->stream>>>(c->ne, c->conn, c->xyz, disp, lambda, mu, ta,
+                                                                           0.0, 0.0, 0.0, c->cooK, nullptr);
+  else if (tangent == KE_BUCKLING_G)
+    k_elem_stiffness<KE_BUCKLING_G><<<grid, KE_THREADS, smem, c->stream>>>(c->ne, c->conn, c->xyz, disp, lambda, mu, ta,
+                                                                           0.0, 0.0, 0.0, c->cooK, nullptr);
   else
-    k_elem_stiffness<false><<<grid, KE_THREADS, smem, c->stream>>>(c->ne, c->conn, c->xyz, disp, lambda, mu, ta,
-                                                                   gx * rho, gy * rho, gz * rho, c->cooK, elv);
+    k_elem_stiffness<KE_ELASTIC><<<grid, KE_THREADS, smem, c->stream>>>(c->ne, c->conn, c->xyz, disp, lambda, mu, ta,
+                                                                        gx * rho, gy * rho, gz * rho, c->cooK, elv);
   c->launches++;
   FCVM_CUDA(cudaGetLastError());
   return FCVM_OK;
@@ -388,7 +426,7 @@ extern "C" int fcvm_assemble(fcvm_ctx *c, int tangent, const double *disp, doubl
   FCVM_CHECK(c->have_bcs, FCVM_E_ARG, "fcvm_assemble: call fcvm_set_constraints first");
   ProfScope ps(c, 4);
   const bool gravity = glv != nullptr;
-  FCVM_TRY(run_elem_stiffness(c, tangent, disp, Et_E, gravity, grav_x, grav_y, grav_z));
+  FCVM_TRY(run_elem_stiffness(c, tangent ? KE_TANGENT : KE_ELASTIC, disp, Et_E, gravity, grav_x, grav_y, grav_z));
   if (gravity) {
     FCVM_TRY(launch_node_gather(c, glv, 1));       // glv += gravity  (fcVM.py:763-767)
     // shared nodes: the caller passes surface loads already summed once; gravity parts are per rank
@@ -419,9 +457,47 @@ extern "C" int fcvm_assemble(fcvm_ctx *c, int tangent, const double *disp, doubl
   return deflation_build(c);       // K Z and (Z^T K Z)^-1 of the second preconditioner level, when switched on
 }
 
+// Matrices of the linear buckling analysis (the nstep == 1 branch of calcTSM, fcVM.py:1002-1006 and 1063-1073, used
+// at fcVM.py:1199-1212): K = elastic stiffness of the undeformed mesh, NOT eliminated -- the diagonal entries of
+// prescribed dofs are multiplied by 100 instead -- and G = -nsm, the geometric stiffness of the stress state in
+// SIG_NEW.  The context's matrix becomes M = K - sigma G (what the shift-invert iteration solves with, through
+// fcvm_pcg_solve: block-Jacobi PCG, no deflation), G goes to a second value array on the same pattern
+// (fcvm_spmv_geometric).
+extern "C" int fcvm_assemble_buckling(fcvm_ctx *c, double sigma) {
+  FCVM_CHECK(c && c->ne > 0 && c->have_bcs, FCVM_E_ARG, "fcvm_assemble_buckling: set the mesh and the constraints first");
+  FCVM_CHECK(c->world == 1, FCVM_E_ARG, "fcvm_assemble_buckling: single GPU only");
+  ProfScope ps(c, 4);
+  if (!c->vals2) FCVM_CUDA(cudaMalloc((void **)&c->vals2, sizeof(double) * 9 * (size_t)c->nblk_stored));
+  FCVM_TRY(run_elem_stiffness(c, KE_BUCKLING_G, nullptr, 0.0, false, 0, 0, 0, sigma));
+  k_coo_reduce<<<(unsigned)c->nslices, SELL_C, 0, c->stream>>>(c->nslices, c->slice_ptr, c->blk_first, c->blk_cnt, c->src,
+                                                              c->cooK, c->vals2);
+  FCVM_TRY(run_elem_stiffness(c, KE_BUCKLING_M, nullptr, 0.0, false, 0, 0, 0, sigma));
+  k_coo_reduce<<<(unsigned)c->nslices, SELL_C, 0, c->stream>>>(c->nslices, c->slice_ptr, c->blk_first, c->blk_cnt, c->src,
+                                                              c->cooK, c->vals);
+  if (!c->diag9) FCVM_CUDA(cudaMalloc((void **)&c->diag9, sizeof(double) * 9 * c->nn));
+  k_extract_diag<<<grid_for(c->nn, 128), 128, 0, c->stream>>>(c->nn, c->diag_pos, c->vals, c->diag9);
+  k_block_inverse<<<grid_for(c->nn, 128), 128, 0, c->stream>>>(c->nn, c->diag9, c->minv);
+  c->launches += 4;
+  FCVM_CUDA(cudaGetLastError());
+  c->assembled = true;
+  c->matrix_elastic = false;
+  c->defl_ready = false;            // the coarse level belongs to the eliminated operator
+  return FCVM_OK;
+}
+
+namespace fcvm {
+int launch_spmv_values(fcvm_ctx *c, const double *vals, const double *x, double *y);
+}
+
+// y = G x with the geometric stiffness of fcvm_assemble_buckling
+extern "C" int fcvm_spmv_geometric(fcvm_ctx *c, const double *x, double *y) {
+  FCVM_CHECK(c && c->vals2 && x && y, FCVM_E_ARG, "fcvm_spmv_geometric: call fcvm_assemble_buckling first");
+  return launch_spmv_values(c, c->vals2, x, y);
+}
+
 extern "C" int fcvm_element_matrices(fcvm_ctx *c, int tangent, const double *disp, double Et_E, double *esm_dev) {
   FCVM_CHECK(c && c->ne > 0 && esm_dev, FCVM_E_ARG, "fcvm_element_matrices: null argument / no mesh");
-  FCVM_TRY(run_elem_stiffness(c, tangent, disp, Et_E, false, 0, 0, 0));
+  FCVM_TRY(run_elem_stiffness(c, tangent ? KE_TANGENT : KE_ELASTIC, disp, Et_E, false, 0, 0, 0));
   k_expand_esm<<<grid_for(c->ne * 900, 256), 256, 0, c->stream>>>(c->ne, c->cooK, esm_dev);
   c->launches++;
   FCVM_CUDA(cudaGetLastError());

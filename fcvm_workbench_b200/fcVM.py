@@ -303,6 +303,80 @@ class Engine:
     def spmv(self, x, y):
         call("fcvm_spmv", self._ctx, ctypes.c_void_p(x), ctypes.c_void_p(y))
 
+    # -- linear buckling analysis (fcVM.py:1199-1212) ----------------------------------------------------------
+    def set_coordinates(self, nocoord):
+        """New nodal coordinates on the same topology (the imperfect geometry, fcVM.py:1240)."""
+        xyz = _np(nocoord, np.float64)
+        assert xyz.shape == self._nocoord.shape
+        self._nocoord = xyz
+        call("fcvm_set_coordinates", self._ctx, _ptr(xyz, f64p))
+        if getattr(self, "_hist", None):
+            self.forget_solutions()
+
+    def assemble_buckling(self, sigma):
+        """K (not eliminated, prescribed diagonals x 100) and G = -nsm of the stress state in SIG_NEW; the
+        engine's matrix becomes K - sigma G (``solve`` / ``spmv``), ``spmv_geometric`` multiplies with G."""
+        if getattr(self, "_hist", None):
+            self.forget_solutions()
+        call("fcvm_assemble_buckling", self._ctx, float(sigma))
+
+    def spmv_geometric(self, x, y):
+        call("fcvm_spmv_geometric", self._ctx, ctypes.c_void_p(x), ctypes.c_void_p(y))
+
+    def buckling_modes(self, k=2, sigma=0.1, tol=1e-11, rtol=1e-12, max_sweeps=200, log=None):
+        """The ``k`` eigenpairs of K x = lambda G x nearest ``sigma`` -- what the reference asks of ARPACK with
+        ``eigsh(K, k=2, M=G, sigma=0.1, which='LM', mode='buckling')`` (fcVM.py:1212) -- by shift-invert subspace
+        iteration on the device: Y = (K - sigma G)^-1 G X (one PCG solve per vector), Rayleigh-Ritz on span(Y)
+        with the Gram matrices Y^T G Y and Y^T (K - sigma G) Y, until the Ritz values stand still.  Needs K - sigma G
+        positive definite (sigma below the first buckling factor); otherwise the PCG reports the breakdown.
+        Returns (eigenvalues ascending, eigenvectors as columns, unit 2-norm, largest component positive)."""
+        import scipy.linalg as sla
+        self.assemble_buckling(sigma)
+        p = max(k + 2, 2 * k)
+        rng = np.random.default_rng(12345)
+        n = self.ndof
+        X = [self.vec(host=rng.standard_normal(n)) for _ in range(p)]
+        W = [self.vec() for _ in range(p)]
+        Y = [self.vec() for _ in range(p)]
+        GY = [self.vec() for _ in range(p)]
+        theta_old = None
+        lam = None
+        for sweep in range(max_sweeps):
+            for j in range(p):
+                self.spmv_geometric(X[j], W[j])                    # W = G X = M Y
+                self.solve(W[j], Y[j], rtol=rtol, max_iter=100000)
+                self.spmv_geometric(Y[j], GY[j])
+            a = np.empty((p, p))
+            b = np.empty((p, p))
+            for i in range(p):
+                for j in range(i, p):
+                    a[i, j] = a[j, i] = self.dot(Y[i], GY[j])
+                    b[i, j] = b[j, i] = 0.5 * (self.dot(Y[i], W[j]) + self.dot(Y[j], W[i]))
+            theta, cvec = sla.eigh(a, b)                           # a c = theta b c, b = Y^T M Y positive definite
+            order = np.argsort(-np.abs(theta))                     # nearest sigma first
+            theta, cvec = theta[order], cvec[:, order]
+            for j in range(p):                                     # X = Y c
+                self.axpby(cvec[0, j], Y[0], 0.0, X[j])
+                for i in range(1, p):
+                    self.axpby(cvec[i, j], Y[i], 1.0, X[j])
+            lam = sigma + 1.0 / theta[:k]
+            if log:
+                log(f"buckling sweep {sweep}: load factors {np.sort(lam)}")
+            if theta_old is not None and np.all(np.abs(theta[:k] - theta_old) <= tol * np.abs(theta[:k])):
+                break
+            theta_old = theta[:k].copy()
+        vec = np.stack([self.get(X[j]) for j in range(k)], axis=1)
+        for v in X + W + Y + GY:
+            call("fcvm_vec_free", self._ctx, ctypes.c_void_p(v))
+            self._vecs.remove(v)
+        order = np.argsort(lam)
+        lam, vec = lam[order], vec[:, order]
+        for j in range(k):
+            vec[:, j] /= np.linalg.norm(vec[:, j])
+            if vec[np.argmax(np.abs(vec[:, j])), j] < 0:
+                vec[:, j] = -vec[:, j]
+        return lam, vec
+
     def matfree_apply(self, x, y):
         """y = K x with the elastic operator recomputed element by element (what the PCG uses for GNLN)."""
         call("fcvm_matfree_apply", self._ctx, ctypes.c_void_p(x), ctypes.c_void_p(y))
@@ -634,13 +708,16 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
     grav = (ctl.grav_x, ctl.grav_y, ctl.grav_z)
     if gnl == "GNLY":                                              # fcVM.py:1087-1097
         LD, relax, disp_output, scale_up = True, 1.0, "total", 1.1
-        if not (float(nstep) > 1.0 and maxImp == 0.0):
-            raise NotImplementedError("eigen-buckling pre-analysis (GNLY with imperfection) is outside this path")
     else:
         LD = False
+    buckling = LD and not (float(nstep) > 1.0 and maxImp == 0.0)  # fcVM.py:1200
+    if buckling and comm is not None and comm.world > 1:
+        raise NotImplementedError("the linear buckling pre-analysis runs on one GPU")
+
+    coords = [m.nocoord]            # replaced by the imperfect geometry after a buckling pre-analysis
 
     def load_vector(disp_host=None):
-        return surface_load_vector(m.nocoord, m.loadfaces, m.pressure, m.loadvertices, m.vertexloads, m.loadedges,
+        return surface_load_vector(coords[0], m.loadfaces, m.pressure, m.loadvertices, m.vertexloads, m.loadedges,
                                    m.edgeloads, m.loadfaces_uni, m.faceloads, disp=disp_host)
 
     glv = eng.vec(host=load_vector())
@@ -674,6 +751,41 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
         eng.update_stress_load(disp_new, ue, qin, Et_E, LD)
         qnorm = eng.masked_norm(qin, m.movdof)                     # ||movdof * qelastic||
 
+    eigenval, eigenvec = None, None
+    nocoord_old = np.array(m.nocoord)
+    if buckling:
+        # linear buckling analysis (fcVM.py:1195-1214): the elastic stress state of the full load, K and G of
+        # calcTSM's nstep == 1 branch, the two load factors nearest 0.1
+        eng.gp_fill(SIG_OLD, 0.0)
+        eng.update_stress_load(zero, ue, qin, Et_E, False, yield_scale=1.0e6)
+        eigenval, eigenvec = eng.buckling_modes(k=2, sigma=0.1, log=say)
+        say(f"buckling load factors: {eigenval}")
+        if float(nstep) != 1.0 and maxImp != 0.0:                  # imperfection and restart, fcVM.py:1224-1294
+            ev1, ev2 = float(ctl.ev1), float(ctl.ev2)
+            ua = ev1 / (ev1 + ev2) * eigenvec[:, 0] + ev2 / (ev1 + ev2) * eigenvec[:, 1]
+            ub = ev1 / (ev1 + ev2) * eigenvec[:, 0] - ev2 / (ev1 + ev2) * eigenvec[:, 1]
+            ma, mb = np.max(np.abs(ua)), np.max(np.abs(ub))
+            if ma > mb:
+                imper = maxImp / ma * np.sign(ua[np.argmax(np.abs(ua))]) * ua
+            else:
+                imper = maxImp / mb * np.sign(ub[np.argmax(np.abs(ub))]) * ub
+            coords[0] = m.nocoord + imper.reshape(-1, 3)           # the imperfect geometry from here on
+            eng.set_coordinates(coords[0])
+            eng.put(glv, load_vector())
+            # back to the eliminated elastic operator, now of the imperfect geometry: calcGSM, factorisation and
+            # elastic solution again, state reset (fcVM.py:1242-1294)
+            if deflation is not None and hasattr(eng, "set_deflation"):
+                eng.set_deflation(deflation)
+            eng.assemble(glv, grav)
+            qnorm = eng.norm(glv)
+            if qnorm < 1.0:
+                qnorm = 1.0
+            eng.residual(1.0, glv, zero, f)
+            eng.axpby(1.0, modf, 1.0, f)
+            eng.solve(f, ue, rtol, max_iter)
+            disp_el = eng.get(ue)
+            dl = dl0
+            eng.axpby(dl, ue, 0.0, du)
     step = -1
     cnt = True
     fail = False
@@ -842,7 +954,7 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
                sigmises=eng.gp_get(SIGMISES), csr=eng.gp_get(CSR), lout=np.asarray(lout), un=np.asarray(un),
                crip=crip_a, peeqplot=np.asarray(peeqplot), pplot=np.asarray(pplot), svmplot=np.asarray(svmplot),
                triaxplot=np.asarray(triaxplot), ecrplot=np.asarray(ecrplot), csrplot=np.asarray(csrplot), fail=fail,
-               nocoord_old=np.array(m.nocoord), lbd=np.asarray(lbd), iters=np.asarray(iters),
+               nocoord_old=nocoord_old, eigenval=eigenval, eigenvec=eigenvec, lbd=np.asarray(lbd), iters=np.asarray(iters),
                nplastic=np.asarray(nplastic), iterat_tot=iterat_tot, pcg_iterations=np.asarray(pcg_its),
                glv=eng.get(glv), modf=eng.get(modf), loadsum=tuple(loadsum), sig_yield=eng.gp_get(SIG_YIELD),
                pgp=eng.gp_get(PGP), sig_test=eng.gp_get(SIG_TEST),

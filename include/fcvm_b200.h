@@ -91,6 +91,9 @@ int fcvm_set_constraints(fcvm_ctx *ctx, const uint8_t *fixmask, const double *fi
 int fcvm_set_interface(fcvm_ctx *ctx, const double *dof_weight, int64_t n_if_local, const int64_t *if_local_node,
                        const int64_t *if_global_slot, int64_t n_if_global);
 
+/* New nodal coordinates on the same topology (nocoord += imper, fcVM.py:1240); assemble again afterwards. */
+int fcvm_set_coordinates(fcvm_ctx *ctx, const double *nocoord);
+
 int64_t fcvm_num_elements(const fcvm_ctx *ctx);
 int64_t fcvm_num_nodes(const fcvm_ctx *ctx);
 
@@ -130,6 +133,13 @@ int fcvm_pgp_count(fcvm_ctx *ctx, int64_t *n_plastic);
  * the geometry nocoord + disp (disp may be NULL). */
 int fcvm_assemble(fcvm_ctx *ctx, int tangent, const double *disp, double Et_E, double grav_x, double grav_y,
                   double grav_z, double *glv);
+/* Linear buckling analysis (calcTSM with nstep == 1, fcVM.py:1002-1006, 1063-1073; used at fcVM.py:1199-1212):
+ * K = elastic stiffness, not eliminated, diagonal entries of prescribed dofs x 100; G = -(geometric stiffness of the
+ * stress state in SIG_NEW).  After the call the context's matrix is K - sigma G (fcvm_pcg_solve / fcvm_spmv work on
+ * it) and fcvm_spmv_geometric multiplies with G: the two operators of the shift-invert eigen-iteration that stands
+ * in for eigsh(K, k, M=G, sigma, mode='buckling').  Single GPU. */
+int fcvm_assemble_buckling(fcvm_ctx *ctx, double sigma);
+int fcvm_spmv_geometric(fcvm_ctx *ctx, const double *x, double *y);
 /* Raw element matrices (ne*900 doubles, device) for element-level parity checks. */
 int fcvm_element_matrices(fcvm_ctx *ctx, int tangent, const double *disp, double Et_E, double *esm_dev);
 /* Lower-triangular CSC of the assembled matrix exactly as scipy builds it at fcVM.py:1111:

@@ -11,7 +11,7 @@ import pytest
 import scipy.sparse as scsp
 import scipy.sparse.linalg as spla
 
-from _golden import ANALYSES, clicks_of, control_of, load, logged_iters, model_of, rel, rel_plot
+from _golden import ANALYSES, BUCKLING, clicks_of, control_of, load, logged_iters, model_of, rel, rel_plot
 
 pytestmark = pytest.mark.gpu
 
@@ -247,6 +247,27 @@ def test_load_displacement_curve_vs_reference_golden(fc, name):
     if name == "tensile":
         x = fc.gauss_point_coordinates(m.elNodes, m.nocoord, [gp_ref])[0]
         assert [float(f"{v:.2e}") for v in x] == [9.31, 7.24, 9.31]                 # tensile.out, last rows
+
+
+@pytest.mark.parametrize("name", BUCKLING)
+def test_buckling_pre_analysis_and_imperfect_restart_vs_reference_golden(fc, name):
+    """GNLY with an imperfection (fcVM.py:1199-1294): linear buckling load factors from the device matrices
+    K (prescribed diagonals x 100, not eliminated) and G (geometric stiffness of the elastic stress state) by
+    shift-invert subspace iteration in place of ARPACK, imperfect geometry from the first mode, restart and
+    large-displacement load stepping -- against the unmodified reference's fixture.  Compared as the oracle is:
+    the square column has a double first mode, so the direction of the imperfection (and with it the mirror image
+    of the fields) is decided by round-off; the load factors, the curves and the scalar histories are not."""
+    z = load(name)
+    m, c = model_of(z), control_of(z)
+    msgs = []
+    o = fc.calcDisp(m, c, clicks=clicks_of(z), rtol=1e-11, log=msgs.append)
+    assert rel(np.sort(o["eigenval"]), np.sort(z["r_eigenval"])) < 1e-8
+    assert logged_iters(msgs) == list(z["r_iters"])
+    for k in ("lout", "un", "peeqplot", "csrplot"):
+        assert rel(o[k], z["r_" + k]) < TOL_CURVE, k
+    sel = np.asarray(z["r_csrplot"]) > 0
+    for k in ("pplot", "svmplot", "triaxplot", "ecrplot"):
+        assert rel_plot(k, o[k], z, sel) < TOL_CURVE, k
 
 
 def test_collapse_analysis_vs_oracle_larger_mesh(fc, oracle):

@@ -9,10 +9,10 @@ import numpy as np
 import pytest
 import scipy.sparse as scsp
 
-from _golden import ANALYSES, ORACLE_ONLY, clicks_of, control_of, load, logged_iters, model_of, rel, rel_plot
+from _golden import ANALYSES, BUCKLING, clicks_of, control_of, load, logged_iters, model_of, rel, rel_plot
 
 
-@pytest.mark.parametrize("name", ANALYSES + ORACLE_ONLY)
+@pytest.mark.parametrize("name", ANALYSES + BUCKLING)
 def test_load_stepping_matches_reference(oracle, name):
     z = load(name)
     m, c = model_of(z), control_of(z)
@@ -22,18 +22,18 @@ def test_load_stepping_matches_reference(oracle, name):
     assert logged_iters(msgs) == list(z["r_iters"]), "Newton iterations per step differ"
     # the buckling case passes through ARPACK, whose iterates depend on the BLAS threading of the day: the
     # imperfection shape is reproduced to ~1e-12 only, and the imperfection-sensitive analysis amplifies that
-    tol_c, tol_f = (1e-6, 1e-5) if name in ORACLE_ONLY else (1e-9, 1e-8)
+    tol_c, tol_f = (1e-6, 1e-5) if name in BUCKLING else (1e-9, 1e-8)
     for k in ("lout", "un", "peeqplot", "csrplot"):
         assert rel(o[k], z["r_" + k]) < tol_c, k
     # state at the Gauss point of max(csr): while csr is still zero everywhere that point is a tie decided by
     # round-off (in the buckling case: by ARPACK's iterates), so those steps are only compared when repeatable
-    sel = np.asarray(z["r_csrplot"]) > 0 if name in ORACLE_ONLY else slice(None)
+    sel = np.asarray(z["r_csrplot"]) > 0 if name in BUCKLING else slice(None)
     for k in ("pplot", "svmplot", "triaxplot", "ecrplot"):
         assert rel_plot(k, o[k], z, sel) < tol_c, k
     # fields: not for the buckling case -- the column is symmetric, so the sign / direction of the imperfection
     # (np.argmax over tied components, fcVM.py:1231-1236) and with it the mirror image of the buckled shape is
     # decided by round-off; the load-displacement curve and the scalar histories above do not depend on it
-    for k in () if name in ORACLE_ONLY else ("displacements", "disp_el", "stresses", "peeq", "sigmises", "csr"):
+    for k in () if name in BUCKLING else ("displacements", "disp_el", "stresses", "peeq", "sigmises", "csr"):
         assert rel(o[k], z["r_" + k]) < tol_f, k
     if name == "tensile":                      # the symmetric cubes have exact ties in argmax(csr)
         assert np.array_equal(o["crip"], z["r_crip"])
