@@ -236,6 +236,184 @@ k_pcg_step(int64_t nn, int it, int defl, const double *__restrict__ w, const dou
   block_reduce_publish<2>(v, red_part, counter, sc, sl);       // gamma_(it+1), rr_(it+1)
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same vector step as a TMA-style stream: the kernel is a pure pass over eleven nodal arrays, so instead of
+// every thread holding its own loads in registers, one elected thread per block moves whole tiles with bulk
+// asynchronous copies (cp.async.bulk global -> shared, completion counted on an mbarrier), the block updates the
+// tile in place in shared memory, and the five result arrays leave through bulk stores (shared -> global, bulk
+// groups).  Two stages per block, two blocks per SM: up to 221 kB of loads in flight per SM with no registers tied
+// up, which is what an HBM3e stream needs.  Persistent grid, tiles dealt round-robin: the order of all sums is
+// fixed.  Tile = 256 nodes: six 6 kB vector pieces and 18 kB of inverse diagonal blocks.
+constexpr int ST_T = 256;
+constexpr int ST_STAGES = 2;
+struct StepTile {
+  double w[3 * ST_T], u[3 * ST_T], p[3 * ST_T], s[3 * ST_T], x[3 * ST_T], r[3 * ST_T], m[9 * ST_T];
+};
+static_assert(sizeof(StepTile) % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(ST_T, 2)
+k_pcg_step_bulk(int64_t nn, int it, int defl, const double *__restrict__ w, const double *__restrict__ minv,
+                const double *__restrict__ wt_, double *x, double *r, double *u, double *p, double *s, double *red_part,
+                unsigned int *counter, double *sc, Slots<2> sl) {
+  extern __shared__ __align__(128) unsigned char st_raw[];
+  StepTile *tiles = (StepTile *)st_raw;
+  __shared__ uint64_t full[ST_STAGES];
+  const int cur = it & 1, prv = cur ^ 1, tid = threadIdx.x;
+  if (sc[S_ITERS] >= 0.0) return;                    // converged earlier in this batch (sticky)
+  if (sc[S_RR + cur] <= sc[S_THR]) {                 // converged after `it` iterations
+    if (blockIdx.x == 0 && tid == 0 && sc[S_ITERS] < 0.0) sc[S_ITERS] = (double)it;
+    return;
+  }
+  const double gam = sc[S_GAMMA + cur];
+  double beta = 0.0, den = sc[S_DELTA];
+  if (it > 0) {
+    const double gprev = sc[S_GAMMA + prv], aprev = sc[S_ALPHA + prv];
+    beta = gprev != 0.0 ? gam / gprev : 0.0;
+    den = sc[S_DELTA] - (aprev != 0.0 ? beta * gam / aprev : 0.0);
+  }
+  if (!(gam > 0.0) || !(den > 0.0)) {                // see k_pcg_step
+    if (blockIdx.x == 0 && tid == 0) {
+      sc[S_STATUS] = (double)PCG_BREAKDOWN;
+      sc[S_ITERS] = (double)it;
+    }
+    return;
+  }
+  const double alpha = gam / den;
+  if (tid == 0) {
+    for (int q = 0; q < ST_STAGES; q++) mbar_init(&full[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t ntiles = nn / ST_T;                  // full tiles; the remainder is walked with plain accesses below
+  auto issue = [&](int64_t t, int stage) {           // thread 0 only
+    StepTile &T = tiles[stage];
+    const int64_t d0 = 3 * t * ST_T;
+    mbar_expect_tx(&full[stage], (uint32_t)sizeof(StepTile));
+    bulk_load(T.w, w + d0, sizeof(T.w), &full[stage]);
+    bulk_load(T.u, u + d0, sizeof(T.u), &full[stage]);
+    bulk_load(T.p, p + d0, sizeof(T.p), &full[stage]);
+    bulk_load(T.s, s + d0, sizeof(T.s), &full[stage]);
+    bulk_load(T.x, x + d0, sizeof(T.x), &full[stage]);
+    bulk_load(T.r, r + d0, sizeof(T.r), &full[stage]);
+    bulk_load(T.m, minv + 9 * t * ST_T, sizeof(T.m), &full[stage]);
+  };
+  double v[2] = {0.0, 0.0};
+  auto node = [&](double *pw, double *pu, double *pp, double *ps, double *px, double *pr, const double *pm, double wgt) {
+    double rn[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const double pc = pu[c] + beta * pp[c];
+      const double sn = pw[c] + beta * ps[c];
+      pp[c] = pc;
+      ps[c] = sn;
+      px[c] += alpha * pc;
+      rn[c] = pr[c] - alpha * sn;
+      pr[c] = rn[c];
+    }
+    const double z0 = pm[0] * rn[0] + pm[1] * rn[1] + pm[2] * rn[2];
+    const double z1 = pm[3] * rn[0] + pm[4] * rn[1] + pm[5] * rn[2];
+    const double z2 = pm[6] * rn[0] + pm[7] * rn[1] + pm[8] * rn[2];
+    pu[0] = z0; pu[1] = z1; pu[2] = z2;
+    if (!defl) v[0] += wgt * (rn[0] * z0 + rn[1] * z1 + rn[2] * z2);
+    v[1] += wgt * (rn[0] * rn[0] + rn[1] * rn[1] + rn[2] * rn[2]);
+  };
+  if (tid == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  int k = 0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, k++) {
+    const int stage = k % ST_STAGES;
+    if (tid == 0 && t + gridDim.x < ntiles) {
+      // the other stage was stored by the previous trip: its bulk stores must have read shared memory
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      issue(t + gridDim.x, stage ^ 1);
+    }
+    mbar_wait(&full[stage], (uint32_t)((k / ST_STAGES) & 1));
+    StepTile &T = tiles[stage];
+    const int64_t n = t * ST_T + tid;
+    node(T.w + 3 * tid, T.u + 3 * tid, T.p + 3 * tid, T.s + 3 * tid, T.x + 3 * tid, T.r + 3 * tid, T.m + 9 * tid,
+         wt_ ? wt_[3 * n] : 1.0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes before the async-proxy reads
+    __syncthreads();
+    if (tid == 0) {
+      const int64_t d0 = 3 * t * ST_T;
+      bulk_store(p + d0, T.p, sizeof(T.p));
+      bulk_store(s + d0, T.s, sizeof(T.s));
+      bulk_store(x + d0, T.x, sizeof(T.x));
+      bulk_store(r + d0, T.r, sizeof(T.r));
+      bulk_store(u + d0, T.u, sizeof(T.u));
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (blockIdx.x == gridDim.x - 1) {                 // the nodes beyond the last full tile
+    const int64_t n = ntiles * ST_T + tid;
+    if (n < nn) {
+      double mm[9];
+#pragma unroll
+      for (int q = 0; q < 9; q++) mm[q] = minv[9 * n + q];
+      double lw[3] = {w[3 * n], w[3 * n + 1], w[3 * n + 2]};
+      node(lw, u + 3 * n, p + 3 * n, s + 3 * n, x + 3 * n, r + 3 * n, mm, wt_ ? wt_[3 * n] : 1.0);
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) sc[S_ALPHA + cur] = alpha;
+  // block partials, then the block that finishes last adds them in block order
+  __shared__ double sm[2][ST_T / 32];
+  __shared__ bool last;
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const double ws = warp_sum(v[i]);
+    if (lane == 0) sm[i][warp] = ws;
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < ST_T / 32; q++) t += sm[i][q];
+      red_part[i * RED_BLOCKS + blockIdx.x] = t;
+    }
+    __threadfence();
+    last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    for (int i = warp; i < 2; i += ST_T / 32) {
+      double t = 0.0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&red_part[i * RED_BLOCKS + b]);
+      t = warp_sum(t);
+      if (lane == 0) sc[sl.s[i]] = t;
+    }
+    if (tid == 0) *counter = 0u;
+  }
+}
+
 // multi-GPU: the three per-rank sums ride at the tail of the interface vector (one all-reduce per iteration)
 __global__ void k_tail_get(const double *__restrict__ tail, double *sc, int gamma_slot, int rr_slot) {
   if (sc[S_ITERS] >= 0.0) return;
@@ -416,6 +594,23 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
     }
     return FCVM_OK;
   };
+  // the vector step as a bulk-copy stream (k_pcg_step_bulk) when every array sits on a 16-byte boundary and the mesh
+  // has full tiles to stream; FCVM_STEP_BULK=0 keeps the register version
+  int step_grid = 0;
+  {
+    static const bool off = getenv("FCVM_STEP_BULK") && atoi(getenv("FCVM_STEP_BULK")) == 0;
+    const uintptr_t all = (uintptr_t)x | (uintptr_t)r | (uintptr_t)u | (uintptr_t)p | (uintptr_t)s | (uintptr_t)wv | (uintptr_t)c->minv;
+    if (!off && (all & 15) == 0 && nn >= 4 * ST_T) {
+      static int sms = 0;
+      if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        FCVM_CUDA(cudaFuncSetAttribute(k_pcg_step_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ST_STAGES * sizeof(StepTile))));
+      }
+      step_grid = (int)std::min<int64_t>(2 * sms, std::min<int64_t>(RED_BLOCKS, nn / ST_T));
+    }
+  }
   int it = 0, n_it = -1;
   const bool fused = pcg_fused_enabled(c);
   if (fused) {
@@ -441,8 +636,12 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
         const int nxt = (it + 1) & 1;
         // deflated: the vector step's own r.u is void (slot L_RU as a sink), gamma comes with the product
         Slots<2> sl = multi ? Slots<2>{{L_RU, L_RR}} : Slots<2>{{defl ? L_RU : S_GAMMA + nxt, S_RR + nxt}};
-        k_pcg_step<<<RED_BLOCKS, RED_THREADS, 0, st>>>(nn, it, defl ? 1 : 0, wv, c->minv, w, x, r, u, p, s, c->red_part,
-                                                       c->red_counter, sc, sl);
+        if (step_grid > 0)
+          k_pcg_step_bulk<<<step_grid, ST_T, ST_STAGES * sizeof(StepTile), st>>>(nn, it, defl ? 1 : 0, wv, c->minv, w, x, r, u, p, s,
+                                                                                c->red_part, c->red_counter, sc, sl);
+        else
+          k_pcg_step<<<RED_BLOCKS, RED_THREADS, 0, st>>>(nn, it, defl ? 1 : 0, wv, c->minv, w, x, r, u, p, s, c->red_part,
+                                                         c->red_counter, sc, sl);
         c->launches++;
       }
       FCVM_TRY(spmv_dot(it + 1));

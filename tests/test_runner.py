@@ -1,0 +1,69 @@
+"""The headless runner ``python -m fcvm_workbench_b200`` end to end on the reference's own ``tensile`` model
+(control file + model bundle in, ``.out`` / ``.vtk`` out): the rows it writes against the rows of the reference's
+committed ``output files/tensile.out`` and against the reference's curve."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from _golden import clicks_of, control_of, load, model_of
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(tmp_path, extra=()):
+    z = load("tensile")
+    m, c = model_of(z), control_of(z)
+    inp, npz = str(tmp_path / "tensile.inp"), str(tmp_path / "tensile.npz")
+    c.write(inp)
+    m.name = "tensile"
+    m.save_npz(npz)
+    clicks = ",".join(f"{e[0]}:{e[1]}" if isinstance(e, tuple) else e for e in clicks_of(z))
+    p = subprocess.run([sys.executable, "-m", "fcvm_workbench_b200", "--inp", inp, "--npz", npz, "--clicks", clicks, "--out",
+                        str(tmp_path), "--rtol", "1e-11", *extra], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, (p.stdout[-2000:], p.stderr[-3000:])
+    return z, m, tmp_path / "tensile.out", tmp_path / "tensile.vtk"
+
+
+def _rows(path):
+    rows = []
+    for ln in open(path):
+        f = ln.split()
+        if len(f) == 12 and f[0].lstrip("-").isdigit():
+            rows.append([float(v) for v in f])
+    return np.array(rows)
+
+
+def _check(z, m, out, vtk):
+    rows = _rows(out)
+    assert len(rows) == len(z["r_lout"])
+    # the reference's curve, at the three digits the file holds
+    for col, key in ((4, "r_lout"), (5, "r_un"), (6, "r_peeqplot"), (11, "r_csrplot")):
+        ref = np.array([float(f"{v:.2e}") for v in z[key]])
+        assert np.allclose(rows[:, col], ref, rtol=1.1e-2, atol=1e-12), key
+    # rows of the reference's committed output files/tensile.out (lines 14-31): Gauss point, load, disp, peeq
+    for i, (_gp, load_, disp, peeq) in {1: (0, 1.00e-01, 1.00e-02, 0.0), 7: (20, 5.00e-01, 5.85e-02, 8.16e-04),
+                                        16: (20, 5.00e-01, 2.60e-01, 1.78e-02)}.items():
+        # (the Gauss-point number is not compared: in this homogeneous tension field max(csr) is a tie between many
+        # points that round-off decides -- see test_load_displacement_curve_vs_reference_golden)
+        assert rows[i, 4] == pytest.approx(load_, rel=1.1e-2) and rows[i, 5] == pytest.approx(disp, rel=1.1e-2)
+        assert rows[i, 6] == pytest.approx(peeq, rel=1.1e-2, abs=1e-12)
+    head = open(out).read().splitlines()[:4]
+    assert head[1].split()[-1] == str(m.ne) and "geometric linear" in head[3]
+    txt = open(vtk).read()
+    assert f"POINTS {m.nn}" in txt and "CELL_TYPES" in txt
+
+
+def test_headless_runner_reproduces_the_reference_output_file(tmp_path):
+    _check(*_run(tmp_path))
+
+
+def test_headless_runner_on_two_gpus(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _check(*_run(tmp_path, ("--gpus", "2")))
