@@ -523,6 +523,7 @@ def main():
         heng = HostEngine(model.elNodes, model.nocoord, model.materialbyElement, model.fix, device=local, comm=hcomm)
         hs, _ = run_sweep(model, ctl, heng, a.warmup, a.steps, a.rtol, barrier, deflation=defl_target)
         hms, hb = hs.ms, [hs.bytes1[0] - hs.bytes0[0], hs.bytes1[1] - hs.bytes0[1]]
+        host_split = {k: round(v, 3) for k, v in sorted(heng.host_seconds.items(), key=lambda kv: -kv[1])}
         if world > 1:
             t = torch.tensor([hms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -533,6 +534,7 @@ def main():
         e2e = {"value": 4 * ne_total * a.steps / (hms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(hb[0] / a.steps), "d2h_bytes_per_step": int(hb[1] / a.steps),
                "ms_per_step": hms / a.steps, "newton_iters_per_s": a.steps / (hms * 1e-3),
+               "host_seconds_whole_sweep": host_split,
                "path": "hostpath.HostEngine: fcvm_host_solve + fcvm_host_update_stress_load on page-locked numpy arrays"
                        + (" (per rank, bytes summed over ranks)" if world > 1 else "")}
         heng.close()

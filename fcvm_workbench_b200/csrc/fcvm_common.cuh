@@ -179,7 +179,8 @@ struct fcvm_ctx {
   int64_t n_items = 0;
   double *item_part = nullptr;  // [n_items][6]
   float *kz32 = nullptr;        // [18][nent]
-  float *einv32 = nullptr;      // [6 ncl][6 ncl]
+  float *einv32 = nullptr;      // [6 ncl][einv_ld]
+  int64_t einv_ld = 0;          // row stride of einv32: 6 ncl rounded up to 4 floats, padding zero
   double *rhs_part = nullptr;   // [RHS_SPLIT][6 ncl] shares of the coarse right-hand side
   int64_t col0 = 0, col1 = 0;   // columns of E^-1 this rank's right-hand side can be non-zero in
   int64_t local_boxes = 0;      // boxes that hold nodes of this rank
@@ -351,6 +352,36 @@ __device__ __forceinline__ double invert_jacobian(const double (&xs)[3][3], doub
   xsi[2][1] = (xs[2][0] * xs[0][1] - xs[0][0] * xs[2][1]) * inv;
   xsi[2][2] = (xs[0][0] * xs[1][1] - xs[1][0] * xs[0][1]) * inv;
   return xsj;
+}
+
+// ---------------------------------------------------------------------------------------
+// Bulk asynchronous copies (the TMA unit without a tensor map: cp.async.bulk, UBLKCP in SASS) and the mbarrier
+// that counts their bytes.  One elected thread issues; everybody waits on the barrier's phase.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
 
 // block-level deterministic sum: fixed tree over the warp, then over warps in order

@@ -243,7 +243,7 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
 // just that column panel and the ranks' products are summed (linearity) -- one exchange instead of two.
 template <typename CT>
 __global__ void __launch_bounds__(256)
-k_gemv(int64_t n, int64_t col0, int64_t col1, const CT *__restrict__ A, const double *__restrict__ x,
+k_gemv(int64_t n, int64_t ld, int64_t col0, int64_t col1, const CT *__restrict__ A, const double *__restrict__ x,
        double *__restrict__ y, const double *__restrict__ sc, int done_slot) {
   if (sc && sc[done_slot] >= 0.0) return;
   __shared__ double part[8];
@@ -251,7 +251,7 @@ k_gemv(int64_t n, int64_t col0, int64_t col1, const CT *__restrict__ A, const do
   const int64_t row = blockIdx.x * 2 + (warp >> 2);
   double s = 0.0;
   if (row < n) {
-    const CT *a = A + row * n;
+    const CT *a = A + row * ld;
     const int64_t w = col1 - col0, c0 = col0 + quarter * w / 4, c1 = col0 + (quarter + 1) * w / 4;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int64_t q = c0 + lane;
@@ -267,6 +267,73 @@ k_gemv(int64_t n, int64_t col0, int64_t col1, const CT *__restrict__ A, const do
   if (lane == 0) part[warp] = s;
   __syncthreads();
   if (row < n && quarter == 0 && lane == 0) y[row] = ((part[warp] + part[warp + 1]) + part[warp + 2]) + part[warp + 3];
+}
+
+// The same product as a bulk-copy stream over the single-precision copy: one block per SM, the panel of x staged
+// once in shared memory, rows of E^-1 arriving RS at a time through an S-stage ring of bulk asynchronous copies
+// (cp.async.bulk + mbarrier) -- the kernel is a pure stream of 4 x rows x columns bytes and the per-warp loads of
+// k_gemv kept only ~25 kB in flight per SM.  Rows dealt round-robin to the blocks; every sum has a fixed shape.
+// ld = row stride in floats (multiple of 4), [col0, col1) multiples of 4.
+template <int RS, int S>
+__global__ void __launch_bounds__(256, 1)
+k_gemv_bulk(int64_t n, int64_t ld, int64_t col0, int64_t col1, const float *__restrict__ A, const double *__restrict__ x,
+            double *__restrict__ y, const double *__restrict__ sc, int done_slot) {
+  if (sc && sc[done_slot] >= 0.0) return;
+  extern __shared__ __align__(128) unsigned char gm_raw[];
+  const int cols = (int)(col1 - col0), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double *xs = (double *)gm_raw;                                   // [cols]
+  float *ring = (float *)(gm_raw + sizeof(double) * (size_t)cols); // [S][RS][cols]
+  __shared__ uint64_t full[S], xbar;
+  __shared__ double red[RS][8];
+  if (tid == 0) {
+    for (int q = 0; q < S; q++) mbar_init(&full[q], 1);
+    mbar_init(&xbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t ngroups = (n + RS - 1) / RS;                       // groups of RS consecutive rows
+  auto issue = [&](int64_t g, int stage) {                         // thread 0 only
+    const int64_t r0 = g * RS;
+    const int nr = (int)min((int64_t)RS, n - r0);
+    mbar_expect_tx(&full[stage], (uint32_t)(nr * cols * sizeof(float)));
+    for (int q = 0; q < nr; q++)
+      bulk_load(ring + ((size_t)stage * RS + q) * cols, A + (r0 + q) * ld + col0, (uint32_t)(cols * sizeof(float)), &full[stage]);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(&xbar, (uint32_t)(cols * sizeof(double)));
+    bulk_load(xs, x + col0, (uint32_t)(cols * sizeof(double)), &xbar);
+    for (int q = 0; q < S; q++)
+      if (blockIdx.x + (int64_t)q * gridDim.x < ngroups) issue(blockIdx.x + (int64_t)q * gridDim.x, q);
+  }
+  mbar_wait(&xbar, 0);
+  int k = 0;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x, k++) {
+    const int stage = k % S;
+    mbar_wait(&full[stage], (uint32_t)((k / S) & 1));
+    const float *a = ring + (size_t)stage * RS * cols;
+    double acc[RS];
+#pragma unroll
+    for (int q = 0; q < RS; q++) acc[q] = 0.0;
+    for (int cidx = tid; cidx < cols; cidx += 256) {
+      const double xv = xs[cidx];
+#pragma unroll
+      for (int q = 0; q < RS; q++) acc[q] += (double)a[(size_t)q * cols + cidx] * xv;
+    }
+#pragma unroll
+    for (int q = 0; q < RS; q++) {
+      const double ws = warp_sum(acc[q]);
+      if (lane == 0) red[q][warp] = ws;
+    }
+    __syncthreads();                                               // every thread has read the stage: it may be refilled
+    if (tid == 0 && g + (int64_t)S * gridDim.x < ngroups) issue(g + (int64_t)S * gridDim.x, stage);
+    if (tid < RS && g * RS + tid < n) {
+      double t = 0.0;
+#pragma unroll
+      for (int wq = 0; wq < 8; wq++) t += red[tid][wq];
+      y[g * RS + tid] = t;
+    }
+    __syncthreads();                                               // red[] is free again
+  }
 }
 
 // out_i = (base ? base_i : 0) + Z_i lam_(cluster of i)
@@ -338,7 +405,9 @@ extern "C" int fcvm_set_deflation(fcvm_ctx *c, int ncx, int ncy, int ncz, const 
   FCVM_CUDA(cudaMemcpy(c->cl_nodes, nodes.data(), sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
   FCVM_TRY(dalloc2(&c->kz_rel, 8 * nn));
   FCVM_TRY(dalloc2(&c->dE, 36 * ncl * ncl)); FCVM_TRY(dalloc2(&c->dEinv, 36 * ncl * ncl));
-  FCVM_TRY(dalloc2(&c->d_rhs, 6 * ncl)); FCVM_TRY(dalloc2(&c->d_lam, 6 * ncl));
+  c->einv_ld = (6 * ncl + 3) / 4 * 4;             // row stride of the single-precision E^-1 (16-byte rows)
+  FCVM_TRY(dalloc2(&c->d_rhs, c->einv_ld)); FCVM_TRY(dalloc2(&c->d_lam, 6 * ncl));
+  FCVM_CUDA(cudaMemset(c->d_rhs, 0, sizeof(double) * c->einv_ld));      // the padding columns stay zero
   FCVM_TRY(dalloc2(&c->rhs_part, RHS_SPLIT * 6 * ncl));
   {
     // Boxes this rank's right-hand side can touch: the boxes of its nodes and their neighbours -- a contiguous
@@ -506,10 +575,28 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
     const bool multi = c->world > 1;
     const int64_t col0 = multi ? c->col0 : 0, col1 = multi ? c->col1 : n6;
     ProfScope ps9(c, 9);
-    if (f32)
-      k_gemv<float><<<grid_for(n6, 2), 256, 0, st>>>(n6, col0, col1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
+    // the panel widened to 16-byte boundaries: the extra columns are zeros of the right-hand side (outside the
+    // hull of this rank's boxes, or padding)
+    const int64_t b0 = col0 / 4 * 4, b1 = std::min<int64_t>((col1 + 3) / 4 * 4, c->einv_ld), bcols = b1 - b0;
+    static const bool no_bulk = getenv("FCVM_GEMV_BULK") && atoi(getenv("FCVM_GEMV_BULK")) == 0;
+    const size_t sm23 = (size_t)bcols * (8 + 3 * 2 * 4), sm12 = (size_t)bcols * (8 + 2 * 1 * 4);
+    if (f32 && !no_bulk && sm12 <= 220 * 1024) {
+      static int sms = 0;
+      if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        FCVM_CUDA(cudaFuncSetAttribute(k_gemv_bulk<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        FCVM_CUDA(cudaFuncSetAttribute(k_gemv_bulk<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      }
+      if (sm23 <= 220 * 1024)
+        k_gemv_bulk<2, 3><<<sms, 256, sm23, st>>>(n6, c->einv_ld, b0, b1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
+      else
+        k_gemv_bulk<1, 2><<<sms, 256, sm12, st>>>(n6, c->einv_ld, b0, b1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
+    } else if (f32)
+      k_gemv<float><<<grid_for(n6, 2), 256, 0, st>>>(n6, c->einv_ld, col0, col1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
     else
-      k_gemv<double><<<grid_for(n6, 2), 256, 0, st>>>(n6, col0, col1, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
+      k_gemv<double><<<grid_for(n6, 2), 256, 0, st>>>(n6, n6, col0, col1, c->dEinv, c->d_rhs, c->d_lam, sc, done_slot);
   }
   if (c->world > 1) {
     // lam = sum over ranks of their products: inside one box a peer-memory exchange (fcvm_p2p.cu: sums in rank

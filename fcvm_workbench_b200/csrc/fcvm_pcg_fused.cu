@@ -54,7 +54,7 @@ struct FusedArgs {
   double *sc;
   // deflation level
   Grid g;
-  int64_t ncl, n6, nent;
+  int64_t ncl, n6, nent, einv_ld;
   int n_items;
   const int32_t *cid, *cl_nodes, *ent_node, *it_box, *it_lo, *it_hi, *box_item_ptr;
   const uint8_t *it_kind;
@@ -173,7 +173,7 @@ __device__ __forceinline__ void coarse_gemv(const FusedArgs &a) {
     const int64_t row = q >> 2;
     const int part = (int)(q & 3);
     const int64_t c0 = part * n6 / 4, c1 = (part + 1) * n6 / 4;
-    const CT *e = E + row * n6;
+    const CT *e = E + row * a.einv_ld;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;            // four loads in flight per lane, fixed interleave
     int64_t col = c0 + lane;
     for (; col + 96 < c1; col += 128) {
@@ -395,6 +395,14 @@ __global__ void k_to_float(int64_t n, const double *__restrict__ src, float *__r
   if (i < n) dst[i] = (float)src[i];
 }
 
+// rows of n doubles -> rows of ld floats, padding zero
+__global__ void k_to_float_rows(int64_t n, int64_t ld, const double *__restrict__ src, float *__restrict__ dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * ld) return;
+  const int64_t r = i / ld, q = i - r * ld;
+  dst[i] = q < n ? (float)src[r * n + q] : 0.0f;
+}
+
 template <typename T>
 int realloc_dev(T **p, int64_t n) {
   if (*p) cudaFree(*p);
@@ -464,11 +472,11 @@ int fused_build_items(fcvm_ctx *c, const std::vector<int32_t> &cl_ptr, const std
 // single-precision copies of K Z and E^-1 for the fused kernel (values change with every assembly)
 int fused_refresh_coarse(fcvm_ctx *c) {
   if (!coarse_fp32()) return FCVM_OK;
-  const int64_t nkz = 18 * c->nent, ne = 36 * c->ncl * c->ncl;
+  const int64_t nkz = 18 * c->nent, n6 = 6 * c->ncl, ne = n6 * c->einv_ld;
   if (!c->kz32) FCVM_TRY(realloc_dev(&c->kz32, nkz));
   if (!c->einv32) FCVM_TRY(realloc_dev(&c->einv32, ne));
   k_to_float<<<grid_for(nkz, 256), 256, 0, c->stream>>>(nkz, c->kz_val, c->kz32);
-  k_to_float<<<grid_for(ne, 256), 256, 0, c->stream>>>(ne, c->dEinv, c->einv32);
+  k_to_float_rows<<<grid_for(ne, 256), 256, 0, c->stream>>>(n6, c->einv_ld, c->dEinv, c->einv32);
   c->launches += 2;
   FCVM_CUDA(cudaGetLastError());
   return FCVM_OK;
@@ -559,6 +567,7 @@ int pcg_fused_loop(fcvm_ctx *c, double *x, int max_iter) {
   if (a.defl) {
     a.g = grid_of(c);
     a.ncl = c->ncl; a.n6 = 6 * c->ncl; a.nent = c->nent;
+    a.einv_ld = f32 ? c->einv_ld : 6 * c->ncl;
     a.n_items = (int)c->n_items;
     a.cid = c->d_cid; a.cl_nodes = c->cl_nodes; a.ent_node = c->ent;
     a.it_box = c->it_box; a.it_lo = c->it_lo; a.it_hi = c->it_hi; a.box_item_ptr = c->box_item_ptr; a.it_kind = c->it_kind;

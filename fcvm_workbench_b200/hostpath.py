@@ -11,7 +11,9 @@ runs either with device-resident state (``fcVM.Engine``) or through the
 host-buffer C ABI (this class).  ``bench.py`` times the latter as its ``e2e`` leg.
 
 Vectors are plain numpy arrays in page-locked memory (``fcvm_host_alloc``); the
-cheap vector algebra between the heavy calls is numpy, as in the reference.
+cheap vector algebra between the heavy calls stays on the host, as in the reference
+(the same arithmetic, run through torch's multi-threaded CPU kernels on views of the
+same memory: at 4.1M dofs single-threaded numpy spent a third of the step there).
 There is no CPU fallback for the heavy calls.
 """
 from __future__ import annotations
@@ -20,12 +22,30 @@ import ctypes
 from typing import Optional
 
 import numpy as np
+import torch
 
 from . import _lib
 from ._lib import call
 from . import fcVM as _fc
 
 _GP6 = (_fc.SIG_OLD, _fc.SIG_NEW, _fc.SIG_TEST)
+
+
+def _timed(fn):
+    """Accumulates the wall time spent in a method (``HostEngine.host_seconds``): where the host-buffer path spends
+    its step -- PCIe copies + kernels inside the heavy calls, numpy algebra between them."""
+    import functools
+    import time
+
+    @functools.wraps(fn)
+    def wrap(self, *a, **k):
+        t0 = time.perf_counter()
+        try:
+            return fn(self, *a, **k)
+        finally:
+            hs = self.__dict__.setdefault("host_seconds", {})
+            hs[fn.__name__] = hs.get(fn.__name__, 0.0) + time.perf_counter() - t0
+    return wrap
 
 
 class HostEngine:
@@ -39,6 +59,8 @@ class HostEngine:
         self._w = comm.part.interface(comm.rank)[0] if comm is not None and comm.world > 1 else None
         self._un_nodes = comm.part.un_nodes(comm.rank) if self._w is not None else None
         self._pinned = []
+        self._tviews = {}
+        self.host_seconds = {}
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         ne = self.ne
@@ -108,69 +130,77 @@ class HostEngine:
     def zero(self, x, n=None):
         x[:] = 0.0
 
+    @_timed
     def copy(self, x, y, n=None):
         y[:] = x
 
-    # in-place forms without temporaries: a fresh 33 MB numpy temporary costs more in page faults than
-    # the arithmetic on it
+    # in-place forms without temporaries, on torch views of the same host memory (multi-threaded)
+    def _tv(self, a):
+        views = self.__dict__.setdefault("_tviews", {})
+        v = views.get(a.ctypes.data)
+        if v is None or v.numel() != a.size:
+            v = views[a.ctypes.data] = torch.from_numpy(a)
+        return v
+
     def _tmp(self, like):
         t = getattr(self, "_scratch", None)
         if t is None or t.shape != like.shape:
-            t = self._scratch = np.empty_like(like)
+            t = self._scratch = torch.empty_like(like)
         return t
 
+    @_timed
     def axpby(self, a, x, b, y, n=None):
         """y = a*x + b*y"""
+        X, Y = self._tv(x), self._tv(y)
         if b == 0.0:
-            np.multiply(x, a, out=y)
+            torch.mul(X, a, out=Y)
         elif a == 0.0:
-            y *= b
+            Y.mul_(b)
         else:
-            t = self._tmp(x)
-            np.multiply(x, a, out=t)
             if b != 1.0:
-                y *= b
-            y += t
+                Y.mul_(b)
+            Y.add_(X, alpha=a)
 
+    @_timed
     def axpbypcz(self, a, x, b, y, c, z, n=None):
         """z = a*x + b*y + c*z"""
-        t = self._tmp(x)
+        X, Y, Z = self._tv(x), self._tv(y), self._tv(z)
         if c == 0.0:
-            np.multiply(x, a, out=z)
+            torch.mul(X, a, out=Z)
         else:
             if c != 1.0:
-                z *= c
-            if a == 1.0:
-                z += x
-            else:
-                np.multiply(x, a, out=t)
-                z += t
-        np.multiply(y, b, out=t)
-        z += t
+                Z.mul_(c)
+            Z.add_(X, alpha=a)
+        Z.add_(Y, alpha=b)
 
     def _gsum(self, v: float) -> float:
         return float(v) if self._w is None else float(sum(self.comm.allgather(float(v))))
 
+    @_timed
     def dot(self, x, y, n=None):
+        X, Y = self._tv(x), self._tv(y)
         if self._w is None:
-            return float(np.dot(x, y))
-        t = self._tmp(x)
-        np.multiply(self._w, x, out=t)
-        return self._gsum(np.dot(t, y))
+            return float(torch.dot(X, Y))
+        t = self._tmp(X)
+        torch.mul(self._tv(self._w), X, out=t)
+        return self._gsum(float(torch.dot(t, Y)))
 
     def norm(self, x):
         return float(np.sqrt(self.dot(x, x)))
 
+    @_timed
     def residual(self, lbd, glv, qin, r):
-        np.multiply(glv, lbd, out=r)
-        r -= qin
-        r *= self._nodal[_fc.FIXDOF]
+        R = self._tv(r)
+        torch.mul(self._tv(glv), lbd, out=R)
+        R.sub_(self._tv(qin))
+        R.mul_(self._tv(self._nodal[_fc.FIXDOF]))
         return self.norm(r)
 
     def masked_norm(self, x, mask_host):
         t = x * np.asarray(mask_host, dtype=np.float64)
         return float(np.sqrt(self._gsum(np.dot(t, t) if self._w is None else np.dot(self._w * t, t))))
 
+    @_timed
     def max_node_disp(self, disp):
         nodes = (self.ndof - 1) // 3 if self._un_nodes is None else self._un_nodes      # fcVM.py:1494-1497
         d = disp[:3 * nodes].reshape(-1, 3)
@@ -179,6 +209,7 @@ class HostEngine:
             m = max(self.comm.allgather(m))
         return float(np.sqrt(m))
 
+    @_timed
     def reaction(self, qin):
         return self._gsum(np.sum(self._movdof * qin) if self._w is None else np.sum(self._w * self._movdof * qin))
 
@@ -194,12 +225,14 @@ class HostEngine:
     def gp_fill(self, which, value):
         self._gp[which][:] = value
 
+    @_timed
     def gp_copy(self, src, dst):
         self._gp[dst][:] = self._gp[src]
 
     def plastic_count(self):
         return int(round(self._gsum(np.count_nonzero(self._pgp))))
 
+    @_timed
     def scale_step_stress(self, fac):
         so = self._gp[_fc.SIG_OLD]
         for w in (_fc.SIG_NEW, _fc.SIG_TEST):
@@ -223,6 +256,7 @@ class HostEngine:
                 call("fcvm_vec_free", d._ctx, ctypes.c_void_p(h))
                 d._vecs.remove(h)
 
+    @_timed
     def solve(self, b, x, rtol=1e-10, max_iter=20000, use_x0=False, raise_on_noconv=True, recycle=False):
         """x = factor(b) (fcVM.py:1130, 1401): one h2d of b, PCG on the device, one d2h of x."""
         self.dev.host_solve(b, rtol, max_iter, out=x, raise_on_noconv=raise_on_noconv)
@@ -231,6 +265,7 @@ class HostEngine:
         self.last_solve = self.dev.last_solve
         return self.last_solve
 
+    @_timed
     def update_stress_load(self, disp_new, du, qin, Et_E, LD=False, yield_scale=1.0):
         """update_stress_load(...) of fcVM.py:2196 with the reference's host arrays."""
         g = self._gp
@@ -242,6 +277,7 @@ class HostEngine:
         self.h2d_bytes += 8 * (4 * ne + 24 * ne + 2 * nd + (nd if disp_new is not None else 0))
         self.d2h_bytes += 8 * (48 * ne + nd) + 4 * ne
 
+    @_timed
     def update_peeq_csr(self, ultimate_strain, Et_E):
         g = self._gp
         res = _fc.update_PEEQ_CSR(self.ne, None, g[_fc.SIG_TEST], g[_fc.SIG_NEW], g[_fc.SIG_YIELD], ultimate_strain,

@@ -371,6 +371,25 @@ def test_bench_workload_at_bench_tolerance_vs_oracle(fc, oracle):
         assert rel(o[k], ref[k]) < TOL_CURVE, k
 
 
+def test_bench_workload_10k_elements_with_box_grid_vs_oracle(fc, oracle):
+    """The same sweep at the largest size the oracle's direct solve finishes in about half a minute (cube n = 12:
+    10,368 elements, 46,875 dofs) with the production solver settings: matrix-free product, deflation over a real
+    5 x 5 x 5 grid of boxes a good two elements wide, single-precision coarse operators, recycled start vectors, bulk-copy
+    vector step, PCG tolerance 1e-8.  Newton iterations per step equal, curves within 1e-6, plastic flags equal
+    away from the yield surface."""
+    import bench
+    m, c = bench.workload(12)                           # ten load steps, 63 Newton iterations, ~40 s of the oracle
+    ref = oracle.calcDisp(m, c)
+    with fc.Engine(m.elNodes, m.nocoord, m.materialbyElement, m.fix) as eng:
+        o = fc.calcDisp(m, c, engine=eng, rtol=1e-8, deflation=bench.DEFLATION)
+        assert eng.deflation_grid == (5, 5, 5)
+    assert list(o["iters"]) == list(ref["iters"]) and sum(o["iters"]) > 20
+    for k in ("lout", "un", "peeqplot"):
+        assert rel(o[k], ref[k]) < TOL_CURVE, k
+    away = np.abs(svm_of(ref["sig_test"]) - ref["sig_yield"]) > 1e-6 * ref["sig_yield"]
+    assert np.array_equal(o["pgp"][away], ref["pgp"][away]) and 0 < o["pgp"].sum() < o["pgp"].size
+
+
 def test_plate_with_hole_collapse_vs_oracle(fc, oracle):
     """BASELINE config 2 analogue: stress concentration at a hole, curved second-order elements,
     mixed elastic/plastic Gauss points, reaction-force load-displacement curve."""
