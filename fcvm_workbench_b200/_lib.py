@@ -84,7 +84,7 @@ _SIGNATURES = {
     "fcvm_host_alloc": [c_int64, POINTER(c_void_p)],
     "fcvm_host_free": [c_void_p],
     "fcvm_host_update_stress_load": [ctxp, f64p, f64p, f64p, f64p, f64p, f64p, f64p, c_double, c_int, u8p],
-    "fcvm_host_solve": [ctxp, f64p, f64p, c_double, c_int, POINTER(c_int), f64p],
+    "fcvm_host_solve": [ctxp, f64p, f64p, c_double, c_int, c_int, POINTER(c_int), f64p],
     "fcvm_timer_start": [ctxp],
     "fcvm_timer_stop_ms": [ctxp, POINTER(c_float)],
     "fcvm_profile_enable": [ctxp, c_int],

@@ -129,6 +129,11 @@ struct fcvm_ctx {
   double *pcg_r = nullptr, *pcg_z = nullptr, *pcg_p = nullptr, *pcg_q = nullptr, *pcg_s = nullptr;
   double *spmv_part = nullptr;  // block partials of the dot product fused into the SpMV
 
+  // recycled start vectors: the last (right-hand side, solution) pairs of solves with the present matrix
+  double *hist_b[2] = {nullptr, nullptr}, *hist_x[2] = {nullptr, nullptr};
+  int hist_n = 0;               // pairs held (0..2), oldest first
+  double hist_gram[2][2] = {{0, 0}, {0, 0}};   // x_i . b_j
+
   // reductions
   double *red_part = nullptr;   // [8][RED_BLOCKS]
   double *red_out = nullptr;    // [16] device scalars

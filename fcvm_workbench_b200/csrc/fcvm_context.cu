@@ -329,6 +329,8 @@ static void free_mesh(fcvm_ctx *c) {
   dfree(c->pcg_r); dfree(c->pcg_z); dfree(c->pcg_p); dfree(c->pcg_q); dfree(c->pcg_s); dfree(c->spmv_part);
   dfree(c->dof_weight); dfree(c->if_node); dfree(c->if_slot); dfree(c->if_buf);
   dfree(c->bslices); dfree(c->islices); dfree(c->tail3);
+  for (int i = 0; i < 2; i++) { dfree(c->hist_b[i]); dfree(c->hist_x[i]); }
+  c->hist_n = 0;
   dfree(c->emask); dfree(c->ga_ticket); dfree(c->ga_group_part); dfree(c->egeo); dfree(c->tile_affine);
   c->n_affine_tiles = 0;
   dfree(c->h_du); dfree(c->h_disp); dfree(c->h_qin); dfree(c->diag9); dfree(c->gp_tmp);

@@ -38,14 +38,14 @@ extern "C" int fcvm_host_update_stress_load(fcvm_ctx *c, const double *sig_yield
 }
 
 // x = factor(b)                                                                fcVM.py:1130, 1401
-extern "C" int fcvm_host_solve(fcvm_ctx *c, const double *b, double *x, double rtol, int max_iter, int *iters,
+extern "C" int fcvm_host_solve(fcvm_ctx *c, const double *b, double *x, double rtol, int max_iter, int recycle, int *iters,
                                double *relres) {
   FCVM_CHECK(c && c->assembled && b && x, FCVM_E_ARG, "fcvm_host_solve: assemble first / null argument");
   const int64_t n3 = 3 * c->nn;
   FCVM_TRY(ensure_vec(c, &c->h_du, n3));
   FCVM_TRY(ensure_vec(c, &c->h_qin, n3));
   FCVM_TRY(fcvm_h2d(c, c->h_du, b, sizeof(double) * n3));
-  int rc = fcvm_pcg_solve(c, c->h_du, c->h_qin, rtol, max_iter, 0, iters, relres);
+  int rc = fcvm_pcg_solve(c, c->h_du, c->h_qin, rtol, max_iter, recycle ? 2 : 0, iters, relres);
   if (rc != FCVM_OK && rc != FCVM_E_NOCONV) return rc;
   FCVM_TRY(fcvm_d2h(c, x, c->h_qin, sizeof(double) * n3));
   return rc;

@@ -441,6 +441,7 @@ extern "C" int fcvm_assemble(fcvm_ctx *c, int tangent, const double *disp, doubl
   // modf needs the unconstrained operator: K * u_fix before rows/columns are eliminated
   c->assembled = true;
   c->matrix_elastic = !tangent && disp == nullptr;
+  c->hist_n = 0;                                   // recycled solutions belong to the previous matrix
   FCVM_TRY(launch_spmv(c, c->fixval, c->pcg_q));
   FCVM_TRY(fcvm_interface_sum(c, c->pcg_q));
   k_apply_constraints<<<(unsigned)c->nslices, SELL_C, 0, c->stream>>>(c->nslices, c->slice_ptr, c->slot_node,
@@ -481,6 +482,7 @@ extern "C" int fcvm_assemble_buckling(fcvm_ctx *c, double sigma) {
   FCVM_CUDA(cudaGetLastError());
   c->assembled = true;
   c->matrix_elastic = false;
+  c->hist_n = 0;
   c->defl_ready = false;            // the coarse level belongs to the eliminated operator
   return FCVM_OK;
 }

@@ -264,8 +264,6 @@ class Engine:
         ``glv`` (device, holding the surface loads) receives the gravity load; ``modf`` is left
         in the named buffer MODF.
         """
-        if getattr(self, "_hist", None):
-            self.forget_solutions()
         try:
             call("fcvm_assemble", self._ctx, 1 if tangent else 0, ctypes.c_void_p(disp) if disp else None, float(Et_E),
                  float(grav[0]), float(grav[1]), float(grav[2]), ctypes.c_void_p(glv) if glv else None)
@@ -310,14 +308,10 @@ class Engine:
         assert xyz.shape == self._nocoord.shape
         self._nocoord = xyz
         call("fcvm_set_coordinates", self._ctx, _ptr(xyz, f64p))
-        if getattr(self, "_hist", None):
-            self.forget_solutions()
 
     def assemble_buckling(self, sigma):
         """K (not eliminated, prescribed diagonals x 100) and G = -nsm of the stress state in SIG_NEW; the
         engine's matrix becomes K - sigma G (``solve`` / ``spmv``), ``spmv_geometric`` multiplies with G."""
-        if getattr(self, "_hist", None):
-            self.forget_solutions()
         call("fcvm_assemble_buckling", self._ctx, float(sigma))
 
     def spmv_geometric(self, x, y):
@@ -381,76 +375,18 @@ class Engine:
         """y = K x with the elastic operator recomputed element by element (what the PCG uses for GNLN)."""
         call("fcvm_matfree_apply", self._ctx, ctypes.c_void_p(x), ctypes.c_void_p(y))
 
-    RECYCLE = 2      # previous (right-hand side, solution) pairs kept for the start vector of the next solve
-
-    def _recycled_start(self, b, x):
-        """Start vector of a repeated solve with the same matrix: the Galerkin projection of the new right-hand
-        side onto the last RECYCLE solutions d_j, whose images K d_j = b_j are known (to the solver tolerance)
-        without another product:  x0 = sum_j y_j d_j  with  (d_i . b_j) y = (d_i . b).  In the modified Newton
-        iteration successive corrections are strongly correlated, so the PCG starts ~0.8 decades closer
-        (measured on the platen sweep).  The stopping test stays relative to ||b||."""
-        h = self._hist
-        m = len(h)
-        if m == 0:
-            return False
-        G = np.empty((m, m))
-        rhs = np.empty(m)
-        for i, (bi, di) in enumerate(h):
-            rhs[i] = self.dot(di, b)
-            for j, (bj, _) in enumerate(h):
-                if j >= i:
-                    key = (i, j)
-                    if key not in self._gram:
-                        self._gram[key] = self.dot(di, bj)
-                    G[i, j] = G[j, i] = self._gram[key]
-        try:
-            y = np.linalg.solve(G, rhs)
-        except np.linalg.LinAlgError:
-            return False
-        if not np.all(np.isfinite(y)):
-            return False
-        self.axpby(y[0], h[0][1], 0.0, x)
-        for k in range(1, m):
-            self.axpby(y[k], h[k][1], 1.0, x)
-        return True
-
-    def _remember(self, b, x):
-        h = self._hist
-        if len(h) == self.RECYCLE:
-            pair = h.pop(0)                          # reuse the oldest pair's storage
-            self._gram = {(i - 1, j - 1): v for (i, j), v in self._gram.items() if i > 0 and j > 0}
-        else:
-            spare = getattr(self, "_spare", [])
-            pair = (spare.pop(), spare.pop()) if len(spare) >= 2 else (self.vec(), self.vec())
-        self.copy(b, pair[0])
-        self.copy(x, pair[1])
-        h.append(pair)
-
-    def forget_solutions(self):
-        """Drop the recycled solutions (the matrix has changed)."""
-        self._gram = {}
-        # the vectors stay allocated for the next pairs
-        self._spare = getattr(self, "_spare", []) + [v for pr in getattr(self, "_hist", []) for v in pr]
-        self._hist = []
-
     def solve(self, b, x, rtol=1e-10, max_iter=20000, use_x0=False, raise_on_noconv=True, recycle=False):
         """x = K^-1 b by preconditioned CG.  Returns (iterations, relative residual).  ``recycle``: start from the
-        projection onto the previous solutions of this matrix and remember this one."""
-        if recycle and not use_x0 and os.environ.get("FCVM_RECYCLE", "1") != "0":
-            if not hasattr(self, "_hist"):
-                self._hist, self._gram = [], {}
-            use_x0 = self._recycled_start(b, x)
+        projection onto the last two solutions of this matrix (kept in the library) and remember this one."""
         it = ctypes.c_int()
         rr = ctypes.c_double()
         rc = call("fcvm_pcg_solve", self._ctx, ctypes.c_void_p(b), ctypes.c_void_p(x), float(rtol), int(max_iter),
-                  1 if use_x0 else 0, ctypes.byref(it), ctypes.byref(rr), allow=(_lib.E_NOCONV,))
+                  1 if use_x0 else (2 if recycle else 0), ctypes.byref(it), ctypes.byref(rr), allow=(_lib.E_NOCONV,))
         if rc == _lib.E_NOCONV and raise_on_noconv:
             raise FcvmError(rc, _lib.cdll().fcvm_last_error().decode())
         self.last_solve = (it.value, rr.value)
         self.pcg_iterations = getattr(self, "pcg_iterations", 0) + it.value
         self.pcg_solves = getattr(self, "pcg_solves", 0) + 1
-        if recycle and rc == 0 and os.environ.get("FCVM_RECYCLE", "1") != "0":
-            self._remember(b, x)
         return it.value, rr.value
 
     def update_stress_load(self, disp_new, du, qin, Et_E, LD=False, yield_scale=1.0):
@@ -541,12 +477,12 @@ class Engine:
              float(Et_E), 1 if LD else 0, _ptr(pg, u8p))
         pgp[:] = pg.astype(bool)
 
-    def host_solve(self, b, rtol=1e-10, max_iter=20000, out=None, raise_on_noconv=True):
+    def host_solve(self, b, rtol=1e-10, max_iter=20000, out=None, raise_on_noconv=True, recycle=False):
         x = np.empty(self.ndof) if out is None else out
         it = ctypes.c_int()
         rr = ctypes.c_double()
         rc = call("fcvm_host_solve", self._ctx, _ptr(_np(b, np.float64), f64p), _ptr(x, f64p), float(rtol),
-                  int(max_iter), ctypes.byref(it), ctypes.byref(rr), allow=(_lib.E_NOCONV,))
+                  int(max_iter), 1 if recycle else 0, ctypes.byref(it), ctypes.byref(rr), allow=(_lib.E_NOCONV,))
         if rc == _lib.E_NOCONV and raise_on_noconv:
             raise FcvmError(rc, _lib.cdll().fcvm_last_error().decode())
         self.last_solve = (it.value, rr.value)

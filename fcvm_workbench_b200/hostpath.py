@@ -259,7 +259,7 @@ class HostEngine:
     @_timed
     def solve(self, b, x, rtol=1e-10, max_iter=20000, use_x0=False, raise_on_noconv=True, recycle=False):
         """x = factor(b) (fcVM.py:1130, 1401): one h2d of b, PCG on the device, one d2h of x."""
-        self.dev.host_solve(b, rtol, max_iter, out=x, raise_on_noconv=raise_on_noconv)
+        self.dev.host_solve(b, rtol, max_iter, out=x, raise_on_noconv=raise_on_noconv, recycle=recycle)
         self.h2d_bytes += b.nbytes
         self.d2h_bytes += x.nbytes
         self.last_solve = self.dev.last_solve

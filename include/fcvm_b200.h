@@ -155,7 +155,9 @@ int fcvm_matfree_apply(fcvm_ctx *ctx, const double *x, double *y);
 
 /* ---- linear solve: replaces factor = cholesky(gsm); x = factor(b) (fcVM.py:1121-1135, 1401) -- */
 /* Preconditioned CG on the device (single-reduction form; block-Jacobi, plus the deflation level below
- * when switched on).  x is overwritten (initial guess zero unless use_x0).  Converged when the
+ * when switched on).  x is overwritten; use_x0 = 0: start from zero, 1: from the x passed in, 2: from the Galerkin
+ * projection of b onto the last two solutions obtained with the present matrix (kept on the device; for the repeated
+ * solves of the modified Newton iteration, fcVM.py:1401) -- and remember this solution.  Converged when the
  * recursively updated residual satisfies ||r|| <= rtol * ||b||; returns FCVM_E_NOCONV after max_iter. */
 int fcvm_pcg_solve(fcvm_ctx *ctx, const double *b, double *x, double rtol, int max_iter, int use_x0, int *iters,
                    double *relres);
@@ -226,8 +228,9 @@ int fcvm_host_free(void *p);
 int fcvm_host_update_stress_load(fcvm_ctx *ctx, const double *sig_yield, const double *disp_new, const double *du,
                                  const double *sig, double *sig_update, double *sig_test_global, double *qin,
                                  double Et_E, int LD, uint8_t *pgp);
-/* x = factor(b)                                                            fcVM.py:1130, 1401 */
-int fcvm_host_solve(fcvm_ctx *ctx, const double *b, double *x, double rtol, int max_iter, int *iters,
+/* x = factor(b)                                                            fcVM.py:1130, 1401
+ * recycle != 0: start from the projection onto the last two solutions with this matrix (see fcvm_pcg_solve). */
+int fcvm_host_solve(fcvm_ctx *ctx, const double *b, double *x, double rtol, int max_iter, int recycle, int *iters,
                     double *relres);
 
 /* ---- timing helpers (CUDA events on the context's stream) ---------------------------------- */
