@@ -54,8 +54,8 @@ def _check(z, m, out, vtk):
         assert rows[i, 6] == pytest.approx(peeq, rel=1.1e-2, abs=1e-12)
     head = open(out).read().splitlines()[:4]
     assert head[1].split()[-1] == str(m.ne) and "geometric linear" in head[3]
-    txt = open(vtk).read()
-    assert f"POINTS {m.nn}" in txt and "CELL_TYPES" in txt
+    txt = open(vtk, "rb").read()                                   # binary VTK 5.1 file
+    assert f"POINTS {m.nn}".encode() in txt and b"CELL_TYPES" in txt
 
 
 def test_headless_runner_reproduces_the_reference_output_file(tmp_path):
