@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--n", type=int, default=55, help="cells per cube edge (elements = 6 n^3)")
     ap.add_argument("--rtol", type=float, default=1e-8, help="PCG relative residual per linear solve")
-    ap.add_argument("--cpu-n", type=int, default=16, help="cube edge of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=14, help="cube edge of the bounded CPU sample")
     ap.add_argument("--deflation", type=int, default=DEFLATION,
                     help="unknowns of the rigid-body-mode coarse level of the PCG preconditioner (0 = block-Jacobi only)")
     ap.add_argument("--scaling", default="strong", choices=("strong", "weak"),
