@@ -138,13 +138,15 @@ __global__ void k_mirror(int64_t n, const double *__restrict__ L, double *__rest
 }
 
 // rhs_c = sum_{i in c} w_i Z_i^T r_i  -  sum_{(i,t) -> c} (K Z)_(i,t)^T y_i        (one block per cluster)
-// RHS_SPLIT blocks per box, each a fixed share of the box's node list and entry list: with one block per box the
-// time of a box (its 1331 nodes and ~4500 entries walked by 256 threads) is a floor that does not shrink when a
-// rank holds only a few boxes.  The block that finishes last adds the shares in order (loads unrolled: no chain
-// of dependent trips) and publishes the right-hand side.
-constexpr int RHS_SPLIT = 4;          // most; one GPU with all boxes runs one block per box (measured faster there)
+// One block of RHS_T threads per box.  The time of a box (its ~1300 nodes and ~4500 entries, every trip a chain
+// entry -> node -> y of dependent loads) is a floor that does not shrink when a rank holds only a few boxes, and
+// with 256 threads it was 18 trips long: 512 threads at two blocks per SM halve it.  Optionally `split` blocks per
+// box (a fixed share of the lists each; the block that finishes last adds the shares in order): measured no faster
+// at any N, kept for boxes far larger than these.
+constexpr int RHS_SPLIT = 4;
+constexpr int RHS_T = 512;
 template <typename CT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RHS_T, 2)
 k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restrict__ cl_nodes,
              const int32_t *__restrict__ ent_ptr, const int32_t *__restrict__ ent_node, const CT *__restrict__ kzs,
              int64_t nent,
@@ -156,7 +158,7 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
   double v[6] = {0, 0, 0, 0, 0, 0};
   const int32_t nb = cl_ptr[c], nlen = cl_ptr[c + 1] - nb;
   const int32_t n0 = nb + (int32_t)((int64_t)nlen * share / split), n1 = nb + (int32_t)((int64_t)nlen * (share + 1) / split);
-  for (int32_t idx = n0 + threadIdx.x; idx < n1; idx += 256) {
+  for (int32_t idx = n0 + threadIdx.x; idx < n1; idx += RHS_T) {
     const int64_t i = cl_nodes[idx];
     double Z[3][6];
     z_of(g, c, xyz, fixdof, i, Z);
@@ -171,8 +173,8 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
     const int32_t eb = ent_ptr[c], elen = ent_ptr[c + 1] - eb;
     const int32_t e1 = eb + (int32_t)((int64_t)elen * (share + 1) / split);
     int32_t idx = eb + (int32_t)((int64_t)elen * share / split) + threadIdx.x;
-    for (; idx + 256 < e1; idx += 512) {
-      const int64_t i = ent_node[idx], j = ent_node[idx + 256];
+    for (; idx + RHS_T < e1; idx += 2 * RHS_T) {
+      const int64_t i = ent_node[idx], j = ent_node[idx + RHS_T];
       const CT *kz = kzs + idx;
       const double y0 = y[3 * i], y1 = y[3 * i + 1], y2 = y[3 * i + 2];
       const double z0 = y[3 * j], z1 = y[3 * j + 1], z2 = y[3 * j + 2];
@@ -180,7 +182,7 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
 #pragma unroll
       for (int q = 0; q < 18; q++) {
         ka[q] = (double)__ldcs(kz + q * nent);
-        kb[q] = (double)__ldcs(kz + q * nent + 256);
+        kb[q] = (double)__ldcs(kz + q * nent + RHS_T);
       }
 #pragma unroll
       for (int m = 0; m < 6; m++) {
@@ -188,7 +190,7 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
         v[m] -= kb[m] * z0 + kb[6 + m] * z1 + kb[12 + m] * z2;
       }
     }
-    for (; idx < e1; idx += 256) {
+    for (; idx < e1; idx += RHS_T) {
       const int64_t i = ent_node[idx];
       const CT *kz = kzs + idx;
       const double y0 = y[3 * i], y1 = y[3 * i + 1], y2 = y[3 * i + 2];
@@ -198,7 +200,7 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
                 (double)__ldcs(kz + (12 + m) * nent) * y2;
     }
   }
-  __shared__ double sm[6][8];
+  __shared__ double sm[6][RHS_T / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int m = 0; m < 6; m++) {
@@ -210,7 +212,7 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
   if (threadIdx.x < 6) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) s += sm[threadIdx.x][w];
+    for (int w = 0; w < RHS_T / 32; w++) s += sm[threadIdx.x][w];
     (split == 1 ? rhs : rhs_part + (int64_t)share * n6)[6 * (int64_t)c + threadIdx.x] = s;
   }
   if (split == 1) return;
@@ -222,16 +224,16 @@ k_coarse_rhs(Grid g, const int32_t *__restrict__ cl_ptr, const int32_t *__restri
   }
   __syncthreads();
   if (last) {
-    for (int64_t q0 = threadIdx.x; q0 < n6; q0 += 4 * 256) {
+    for (int64_t q0 = threadIdx.x; q0 < n6; q0 += 4 * RHS_T) {
       double p[4][RHS_SPLIT];
 #pragma unroll
       for (int t = 0; t < 4; t++)
 #pragma unroll
         for (int k = 0; k < RHS_SPLIT; k++)
-          p[t][k] = (k < split && q0 + 256 * t < n6) ? __ldcg(rhs_part + k * n6 + q0 + 256 * t) : 0.0;
+          p[t][k] = (k < split && q0 + RHS_T * t < n6) ? __ldcg(rhs_part + k * n6 + q0 + RHS_T * t) : 0.0;
 #pragma unroll
       for (int t = 0; t < 4; t++)
-        if (q0 + 256 * t < n6) rhs[q0 + 256 * t] = ((p[t][0] + p[t][1]) + p[t][2]) + p[t][3];
+        if (q0 + RHS_T * t < n6) rhs[q0 + RHS_T * t] = ((p[t][0] + p[t][1]) + p[t][2]) + p[t][3];
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }
@@ -559,14 +561,14 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
   const bool f32 = coarse_fp32() && c->kz32 && c->einv32;
   {
   ProfScope ps8(c, 8);
-  // several blocks per box only when this rank holds too few boxes to fill the GPU with one block each
-  const int split = c->local_boxes < 800 ? RHS_SPLIT : 1;
+  static const int split_env = getenv("FCVM_RHS_SPLIT") ? std::max(1, std::min(RHS_SPLIT, atoi(getenv("FCVM_RHS_SPLIT")))) : 1;
+  const int split = split_env;
   if (f32)
-    k_coarse_rhs<float><<<(unsigned)(split * c->ncl), 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz32,
+    k_coarse_rhs<float><<<(unsigned)(split * c->ncl), RHS_T, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz32,
                                                                    c->nent, c->xyz, fixdof, c->dof_weight, r, y, c->d_rhs,
                                                                    c->rhs_part, c->red_counter + 3, split, sc, done_slot);
   else
-    k_coarse_rhs<double><<<(unsigned)(split * c->ncl), 256, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val,
+    k_coarse_rhs<double><<<(unsigned)(split * c->ncl), RHS_T, 0, st>>>(g, c->cl_ptr, c->cl_nodes, c->ent_ptr, c->ent, c->kz_val,
                                                                     c->nent, c->xyz, fixdof, c->dof_weight, r, y, c->d_rhs,
                                                                     c->rhs_part, c->red_counter + 3, split, sc, done_slot);
   }
