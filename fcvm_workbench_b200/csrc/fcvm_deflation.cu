@@ -430,6 +430,14 @@ extern "C" int fcvm_set_deflation(fcvm_ctx *c, int ncx, int ncy, int ncz, const 
   return FCVM_OK;
 }
 
+// boxes and stored (node, box) entries of K Z (roofline arithmetic of the coarse kernels)
+extern "C" int fcvm_deflation_stats(fcvm_ctx *c, int64_t *boxes, int64_t *entries) {
+  FCVM_CHECK(c, FCVM_E_ARG, "null context");
+  if (boxes) *boxes = c->ncl;
+  if (entries) *entries = c->defl_structure ? c->nent : 0;
+  return FCVM_OK;
+}
+
 namespace fcvm {
 
 int fused_build_items(fcvm_ctx *c, const std::vector<int32_t> &cl_ptr, const std::vector<int32_t> &ent_ptr);

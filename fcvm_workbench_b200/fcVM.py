@@ -462,6 +462,11 @@ class Engine:
     def launch_count(self) -> int:
         return int(call("fcvm_launch_count", self._ctx))
 
+    def deflation_stats(self):
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        call("fcvm_deflation_stats", self._ctx, ctypes.byref(a), ctypes.byref(b))
+        return dict(boxes=a.value, entries=b.value)
+
     def matrix_stats(self):
         a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         call("fcvm_matrix_stats", self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))

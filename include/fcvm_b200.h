@@ -176,6 +176,9 @@ int fcvm_pcg_phase_times(fcvm_ctx *ctx, double *ms6, int64_t *iterations, int re
 int fcvm_set_deflation(fcvm_ctx *ctx, int ncx, int ncy, int ncz, const int32_t *cid, const double *lo,
                        const double *h, const uint8_t *active);
 
+/* Boxes and stored (node, box) entries of K Z, for the roofline arithmetic of the coarse kernels. */
+int fcvm_deflation_stats(fcvm_ctx *ctx, int64_t *boxes, int64_t *entries);
+
 /* ---- stress update: update_stress_load (fcVM.py:2196-2464) ---------------------------------- */
 /* Reads SIG_OLD / SIG_YIELD, writes SIG_NEW / SIG_TEST / PGP, and qin = internal force vector
  * (overwritten, not accumulated: the reference always passes zeros, fcVM.py:1324, 1441).
