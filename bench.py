@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
-    ap.add_argument("--n", type=int, default=55, help="cells per cube edge (elements = 6 n^3)")
+    ap.add_argument("--n", "--cells", dest="n", type=int, default=55, help="cells per cube edge (elements = 6 n^3)")
     ap.add_argument("--rtol", type=float, default=1e-8, help="PCG relative residual per linear solve")
     ap.add_argument("--cpu-n", type=int, default=14, help="cube edge of the bounded CPU sample")
     ap.add_argument("--deflation", type=int, default=DEFLATION,
@@ -456,7 +456,8 @@ def main():
             sk.bind(("127.0.0.1", 0))
             port = sk.getsockname()[1]
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
-               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + \
+            ["--cells" if v == "--n" else v for v in sys.argv[1:]]      # torchrun's parser takes "--n" for an abbreviation of its own
         return subprocess.call(cmd)
     import torch
     if not torch.cuda.is_available():
