@@ -589,20 +589,29 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
     // hull of this rank's boxes, or padding)
     const int64_t b0 = col0 / 4 * 4, b1 = std::min<int64_t>((col1 + 3) / 4 * 4, c->einv_ld), bcols = b1 - b0;
     static const bool no_bulk = getenv("FCVM_GEMV_BULK") && atoi(getenv("FCVM_GEMV_BULK")) == 0;
-    const size_t sm23 = (size_t)bcols * (8 + 3 * 2 * 4), sm12 = (size_t)bcols * (8 + 2 * 1 * 4);
-    if (f32 && !no_bulk && sm12 <= 220 * 1024) {
+    // rows per stage: as many as the panel leaves room for in 220 kB of shared memory (narrow panels of a rank
+    // with few boxes would otherwise pay a barrier per two short rows)
+    const size_t smem_cap = 220 * 1024;
+    auto need = [&](int rs, int stages) { return (size_t)bcols * (8 + (size_t)stages * rs * 4); };
+    if (f32 && !no_bulk && need(1, 2) <= smem_cap) {
       static int sms = 0;
       if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        FCVM_CUDA(cudaFuncSetAttribute(k_gemv_bulk<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        FCVM_CUDA(cudaFuncSetAttribute(k_gemv_bulk<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        FCVM_CUDA(cudaFuncSetAttribute(k_gemv_bulk<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        FCVM_CUDA(cudaFuncSetAttribute(k_gemv_bulk<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        FCVM_CUDA(cudaFuncSetAttribute(k_gemv_bulk<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        FCVM_CUDA(cudaFuncSetAttribute(k_gemv_bulk<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
       }
-      if (sm23 <= 220 * 1024)
-        k_gemv_bulk<2, 3><<<sms, 256, sm23, st>>>(n6, c->einv_ld, b0, b1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
+      if (need(8, 3) <= smem_cap)
+        k_gemv_bulk<8, 3><<<sms, 256, need(8, 3), st>>>(n6, c->einv_ld, b0, b1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
+      else if (need(4, 3) <= smem_cap)
+        k_gemv_bulk<4, 3><<<sms, 256, need(4, 3), st>>>(n6, c->einv_ld, b0, b1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
+      else if (need(2, 3) <= smem_cap)
+        k_gemv_bulk<2, 3><<<sms, 256, need(2, 3), st>>>(n6, c->einv_ld, b0, b1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
       else
-        k_gemv_bulk<1, 2><<<sms, 256, sm12, st>>>(n6, c->einv_ld, b0, b1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
+        k_gemv_bulk<1, 2><<<sms, 256, need(1, 2), st>>>(n6, c->einv_ld, b0, b1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
     } else if (f32)
       k_gemv<float><<<grid_for(n6, 2), 256, 0, st>>>(n6, c->einv_ld, col0, col1, c->einv32, c->d_rhs, c->d_lam, sc, done_slot);
     else
