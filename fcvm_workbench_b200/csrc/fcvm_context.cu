@@ -704,7 +704,10 @@ extern "C" int fcvm_interface_sum(fcvm_ctx *c, double *v) {
 
 namespace fcvm {
 // the exchange on the communication stream (the caller orders it against the compute stream with events)
-int interface_sum_on_comm_stream(fcvm_ctx *c, double *v) { return interface_sum_impl(c, v, c->comm_stream); }
+int interface_sum_on_comm_stream(fcvm_ctx *c, double *v) {
+  if (c && c->world > 1 && c->n_if_global == 0) return FCVM_OK;      // a partition without shared nodes
+  return interface_sum_impl(c, v, c->comm_stream);
+}
 }
 
 // ---- vectors ----------------------------------------------------------------------------

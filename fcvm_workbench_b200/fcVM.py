@@ -520,20 +520,29 @@ def deflation_boxes(lo, hi, elem_extent, target_unknowns=3072, grid=None):
 # repeated calls -- the reference calls update_stress_load once per Newton iteration -- reuse
 # the resident connectivity and sparsity pattern.
 # ----------------------------------------------------------------------------------------------
-_engine_cache = {}
+_engine_cache = {}          # insertion-ordered: the oldest engine is evicted first
+
+
+def _mesh_key(el, xyz, mat, device):
+    """Identity of a mesh for the engine cache.  The reference hands the same arrays to update_stress_load on every
+    Newton iteration, so the key must be cheap: shapes, material, and a strided sample of connectivity and
+    coordinates (a few thousand values whatever the mesh size) instead of a hash over ~100 MB."""
+    se = el.reshape(-1)[::max(1, el.size // 4096)]
+    sx = xyz.reshape(-1)[::max(1, xyz.size // 4096)]
+    return (el.shape, xyz.shape, hash(se.tobytes()), hash(sx.tobytes()), float(el.sum()), float(xyz.sum()),
+            float(mat[0][0]), float(mat[0][1]), float(mat[0][2]), device)
 
 
 def _engine_for(elNodes, nocoord, materialbyElement, fix=None, device=0) -> Engine:
     el = np.asarray(elNodes)
     xyz = np.asarray(nocoord)
     mat = np.asarray(materialbyElement, dtype=np.float64)
-    key = (el.shape, xyz.shape, hash(el.tobytes()), hash(xyz.tobytes()), float(mat[0][0]), float(mat[0][1]),
-           float(mat[0][2]), device)
+    key = _mesh_key(el, xyz, mat, device)
     eng = _engine_cache.get(key)
     if eng is None:
         if len(_engine_cache) >= 4:
-            _, old = _engine_cache.popitem()
-            old.close()
+            oldest = next(iter(_engine_cache))
+            _engine_cache.pop(oldest).close()
         eng = Engine(el, xyz, mat, device=device)
         _engine_cache[key] = eng
     if fix is not None:
@@ -561,6 +570,8 @@ def calcGSM(elNodes, nocoord, materialbyElement, fix, grav_x, grav_y, grav_z, lo
     col = np.repeat(np.arange(eng.ndof, dtype=np.int64), np.diff(indptr))
     glv_h = eng.get(glv)
     modf = eng.get(eng.buf(MODF))
+    call("fcvm_vec_free", eng._ctx, ctypes.c_void_p(glv))
+    eng._vecs.remove(glv)
     ls = glv_h.reshape(-1, 3).sum(axis=0)
     x = gauss_point_coordinates(elNodes, nocoord)
     V = float("nan")          # "Element volume - not used" (fcVM.py:760)
