@@ -204,6 +204,12 @@ struct fcvm_ctx {
   // host staging / device scratch of fcvm_host_*
   double *gp_tmp = nullptr;     // [24*ne] device scratch of the Gauss-point layout conversions
   double *h_du = nullptr, *h_disp = nullptr, *h_qin = nullptr;
+  // pipelined fcvm_host_update_stress_load: full-size device staging in the reference layout (sig 24 + sig_yield 4
+  // in, sig_new 24 + sig_test 24 out, flags), a copy-in and a copy-out stream, one event pair per chunk
+  double *hs_in = nullptr, *hs_out = nullptr;
+  uint8_t *hs_pgp = nullptr;
+  cudaStream_t h_in_stream = nullptr, h_out_stream = nullptr;
+  cudaEvent_t h_ev_in[16] = {nullptr}, h_ev_k[16] = {nullptr};
   double *diag9 = nullptr;      // [3][nn][3] assembled diagonal blocks, row-wise
 };
 

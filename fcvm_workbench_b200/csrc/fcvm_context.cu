@@ -226,6 +226,48 @@ __global__ void k_pgp_soa_to_aos(int64_t ne, const uint8_t *__restrict__ soa, ui
   aos[i] = soa[(i & 3) * ne + (i >> 2)];
 }
 
+// the same conversions for the elements [a, b) only (chunks of the pipelined host-buffer path); the AoS side is a
+// full-size staging array, so indices are absolute
+__global__ void k_gp_aos_to_soa_range(int64_t ne, int64_t a, int64_t b, int ncomp, const double *__restrict__ aos, double *soa) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, len = b - a;
+  if (t >= len * 4 * ncomp) return;
+  const int64_t el = a + t % len, q = t / len;
+  const int ip = (int)(q & 3), c = (int)(q >> 2);
+  soa[q * ne + el] = aos[(4 * el + ip) * ncomp + c];
+}
+__global__ void k_gp_soa_to_aos_range(int64_t ne, int64_t a, int64_t b, int ncomp, const double *__restrict__ soa, double *aos) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (b - a) * 4 * ncomp) return;
+  const int64_t i = 4 * a * ncomp + t;                 // absolute AoS index
+  const int c = (int)(i % ncomp);
+  const int64_t g = i / ncomp;
+  aos[i] = soa[((int64_t)c * 4 + (g & 3)) * ne + (g >> 2)];
+}
+__global__ void k_pgp_soa_to_aos_range(int64_t ne, int64_t a, int64_t b, const uint8_t *__restrict__ soa, uint8_t *aos) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= 4 * (b - a)) return;
+  const int64_t i = 4 * a + t;
+  aos[i] = soa[(i & 3) * ne + (i >> 2)];
+}
+
+namespace fcvm {
+int launch_gp_in(fcvm_ctx *c, int64_t a, int64_t b, int ncomp, const double *aos, double *soa) {
+  k_gp_aos_to_soa_range<<<grid_for((b - a) * 4 * ncomp, 256), 256, 0, c->stream>>>(c->ne, a, b, ncomp, aos, soa);
+  c->launches++;
+  return FCVM_OK;
+}
+int launch_gp_out(fcvm_ctx *c, int64_t a, int64_t b, int ncomp, const double *soa, double *aos) {
+  k_gp_soa_to_aos_range<<<grid_for((b - a) * 4 * ncomp, 256), 256, 0, c->stream>>>(c->ne, a, b, ncomp, soa, aos);
+  c->launches++;
+  return FCVM_OK;
+}
+int launch_pgp_out(fcvm_ctx *c, int64_t a, int64_t b, const uint8_t *soa, uint8_t *aos) {
+  k_pgp_soa_to_aos_range<<<grid_for(4 * (b - a), 256), 256, 0, c->stream>>>(c->ne, a, b, soa, aos);
+  c->launches++;
+  return FCVM_OK;
+}
+}  // namespace fcvm
+
 __global__ void k_fill(int64_t n, double v, double *x) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) x[i] = v;
@@ -333,6 +375,7 @@ static void free_mesh(fcvm_ctx *c) {
   c->hist_n = 0;
   dfree(c->emask); dfree(c->ga_ticket); dfree(c->ga_group_part); dfree(c->egeo); dfree(c->tile_affine);
   c->n_affine_tiles = 0;
+  dfree(c->hs_in); dfree(c->hs_out); dfree(c->hs_pgp);
   dfree(c->h_du); dfree(c->h_disp); dfree(c->h_qin); dfree(c->diag9); dfree(c->gp_tmp);
   c->assembled = false;
   c->have_bcs = false;
@@ -355,6 +398,12 @@ extern "C" int fcvm_destroy(fcvm_ctx *c) {
   if (c->cus_work) cudaFree(c->cus_work);
   if (c->cus_info) cudaFree(c->cus_info);
   if (c->phase_ns) cudaFree(c->phase_ns);
+  if (c->h_in_stream) cudaStreamDestroy(c->h_in_stream);
+  if (c->h_out_stream) cudaStreamDestroy(c->h_out_stream);
+  for (int i = 0; i < 16; i++) {
+    if (c->h_ev_in[i]) cudaEventDestroy(c->h_ev_in[i]);
+    if (c->h_ev_k[i]) cudaEventDestroy(c->h_ev_k[i]);
+  }
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);

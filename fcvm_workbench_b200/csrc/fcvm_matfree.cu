@@ -181,7 +181,10 @@ __global__ void k_tile_affine(int64_t ne, const uint8_t *__restrict__ affine, ui
 }
 
 // the product on a tile of straight-sided elements (same layout and order of operations as k_elastic_apply)
-__global__ void __launch_bounds__(MF_THREADS, 10)
+#ifndef MF_AFF_MINB
+#define MF_AFF_MINB 10
+#endif
+__global__ void __launch_bounds__(MF_THREADS, MF_AFF_MINB)
 k_elastic_apply_affine(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ egeo,
                        const uint8_t *__restrict__ tile_affine, const double *__restrict__ x,
                        const uint32_t *__restrict__ emask, double lambda, double mu, double *__restrict__ elv,

@@ -135,11 +135,11 @@ k_stress_update(int64_t ne, const int32_t *__restrict__ conn, const double *__re
                 const double *__restrict__ disp, const double *__restrict__ du, Material m,
                 const double *__restrict__ sig_old, const double *__restrict__ sig_yield, double yield_scale,
                 double *__restrict__ sig_new, double *__restrict__ sig_test, uint8_t *__restrict__ pgp,
-                double *__restrict__ elv) {
+                double *__restrict__ elv, int tile0) {
   __shared__ double smem[4 * 30 * SU_PAD];        // nodal staging [2][32][35], then force staging [4][30][33]
   double *sX = smem, *sU = smem + SU_E * SU_ROW;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t e0 = (int64_t)blockIdx.x * SU_E;
+  const int64_t e0 = ((int64_t)blockIdx.x + tile0) * SU_E;
   const bool live = e0 + lane < ne;
   const int64_t e = min(e0 + lane, ne - 1);
   // the Gauss-point state is requested first, so that its HBM latency overlaps the gather and the kinematics
@@ -216,11 +216,11 @@ k_stress_update_pair(int64_t ne, const int32_t *__restrict__ conn, const double 
                      const double *__restrict__ disp, const double *__restrict__ du, Material m,
                      const double *__restrict__ sig_old, const double *__restrict__ sig_yield, double yield_scale,
                      double *__restrict__ sig_new, double *__restrict__ sig_test, uint8_t *__restrict__ pgp,
-                     double *__restrict__ elv) {
+                     double *__restrict__ elv, int tile0) {
   __shared__ double smem[2 * SU_E * SU_ROW];      // nodal staging [2][32][35], then force staging [2][30][33]
   double *sX = smem, *sU = smem + SU_E * SU_ROW;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t e0 = (int64_t)blockIdx.x * SU_E;
+  const int64_t e0 = ((int64_t)blockIdx.x + tile0) * SU_E;
   const bool live = e0 + lane < ne;
   const int64_t e = min(e0 + lane, ne - 1);
   const int gpa = 2 * warp, gpb = gpa + 1;
@@ -325,36 +325,43 @@ int launch_node_gather(fcvm_ctx *c, double *out, int accumulate) {
 }
 }  // namespace fcvm
 
-extern "C" int fcvm_update_stress_load(fcvm_ctx *c, const double *disp_new, const double *du, double *qin,
-                                       double Et_E, int LD, double yield_scale) {
-  FCVM_CHECK(c && c->ne > 0 && du && qin, FCVM_E_ARG, "fcvm_update_stress_load: null argument / no mesh");
-  FCVM_CHECK(!LD || disp_new, FCVM_E_ARG, "fcvm_update_stress_load: LD needs disp_new");
+namespace fcvm {
+// the Gauss-point pass over the 32-element tiles [tile0, tile0 + ntiles): element vectors to the scratch
+int launch_stress_tiles(fcvm_ctx *c, const double *disp_new, const double *du, double Et_E, int LD, double yield_scale,
+                        int64_t tile0, int64_t ntiles) {
   const Material m = make_material(c->E, c->nu, Et_E);
   const double *so = (const double *)c->buf[FCVM_BUF_SIG_OLD], *sy = (const double *)c->buf[FCVM_BUF_SIG_YIELD];
   double *sn = (double *)c->buf[FCVM_BUF_SIG_NEW], *stt = (double *)c->buf[FCVM_BUF_SIG_TEST];
   uint8_t *pg = (uint8_t *)c->buf[FCVM_BUF_PGP];
-  {
-    ProfScope ps(c, 1);
-    const int grid = grid_for(c->ne, SU_E);
-    // default: two Gauss points per thread (0.265 ms at 1M elements); FCVM_STRESS_PAIR=0 selects the
-    // four-warp kernel (0.277 ms) for comparison
-    static const bool pair = !(getenv("FCVM_STRESS_PAIR") && atoi(getenv("FCVM_STRESS_PAIR")) == 0);
-    if (pair) {
-      if (LD)
-        k_stress_update_pair<true><<<grid, SP_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
-                                                                     yield_scale, sn, stt, pg, c->elv);
-      else
-        k_stress_update_pair<false><<<grid, SP_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
-                                                                      yield_scale, sn, stt, pg, c->elv);
-    } else if (LD)
-      k_stress_update<true><<<grid, SU_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
-                                                                yield_scale, sn, stt, pg, c->elv);
+  ProfScope ps(c, 1);
+  const int grid = (int)ntiles, t0 = (int)tile0;
+  // default: two Gauss points per thread (0.265 ms at 1M elements); FCVM_STRESS_PAIR=0 selects the
+  // four-warp kernel (0.277 ms) for comparison
+  static const bool pair = !(getenv("FCVM_STRESS_PAIR") && atoi(getenv("FCVM_STRESS_PAIR")) == 0);
+  if (pair) {
+    if (LD)
+      k_stress_update_pair<true><<<grid, SP_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
+                                                                   yield_scale, sn, stt, pg, c->elv, t0);
     else
-      k_stress_update<false><<<grid, SU_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
-                                                                 yield_scale, sn, stt, pg, c->elv);
-    c->launches++;
-    FCVM_CUDA(cudaGetLastError());
-  }
+      k_stress_update_pair<false><<<grid, SP_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
+                                                                    yield_scale, sn, stt, pg, c->elv, t0);
+  } else if (LD)
+    k_stress_update<true><<<grid, SU_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
+                                                              yield_scale, sn, stt, pg, c->elv, t0);
+  else
+    k_stress_update<false><<<grid, SU_THREADS, 0, c->stream>>>(c->ne, c->conn, c->xyz, disp_new, du, m, so, sy,
+                                                               yield_scale, sn, stt, pg, c->elv, t0);
+  c->launches++;
+  FCVM_CUDA(cudaGetLastError());
+  return FCVM_OK;
+}
+}  // namespace fcvm
+
+extern "C" int fcvm_update_stress_load(fcvm_ctx *c, const double *disp_new, const double *du, double *qin,
+                                       double Et_E, int LD, double yield_scale) {
+  FCVM_CHECK(c && c->ne > 0 && du && qin, FCVM_E_ARG, "fcvm_update_stress_load: null argument / no mesh");
+  FCVM_CHECK(!LD || disp_new, FCVM_E_ARG, "fcvm_update_stress_load: LD needs disp_new");
+  FCVM_TRY(launch_stress_tiles(c, disp_new, du, Et_E, LD, yield_scale, 0, grid_for(c->ne, SU_E)));
   FCVM_TRY(launch_node_gather(c, qin, 0));
   return fcvm_interface_sum(c, qin);
 }
