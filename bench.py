@@ -581,9 +581,13 @@ def main():
             "setup_s": {"mesh": round(t_mesh, 2)},
         }
         print(json.dumps(line))
+    bad = bool(check.get("vs_single_gpu")) and not check["vs_single_gpu"]["ok"]
+    if bad and rank == 0:
+        print("bench.py: the history of this sweep differs from the committed single-GPU trace by more than 1e-6 "
+              f"({check['vs_single_gpu']})", file=sys.stderr)
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 1 if bad else 0
 
 
 if __name__ == "__main__":

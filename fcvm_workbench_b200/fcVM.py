@@ -672,6 +672,9 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
         return surface_load_vector(coords[0], m.loadfaces, m.pressure, m.loadvertices, m.vertexloads, m.loadedges,
                                    m.edgeloads, m.loadfaces_uni, m.faceloads, disp=disp_host)
 
+    # follower loads: only surface / edge / vertex loads depend on the displaced geometry (calcTSM, fcVM.py:856-938);
+    # without any the large-displacement branch keeps its load vector on the device
+    has_loads = any(len(t) > 1 for t in (m.loadfaces, m.loadfaces_uni, m.loadedges, m.loadvertices))
     glv = eng.vec(host=load_vector())
     eng.assemble(glv, grav)                                        # calcGSM
     modf, fixdof = eng.buf(MODF), eng.buf(FIXDOF)
@@ -799,7 +802,10 @@ def calcDisp(model, ctl, clicks=(), device=0, rtol=1e-10, max_iter=50000, log=No
                     iterat += 1
                     iterat_tot += 1
                     if LD and (iterat == 1 or eng.plastic_count() > 0):       # fcVM.py:1351-1396
-                        eng.put(glv, load_vector(eng.get(disp_new)))
+                        if has_loads:
+                            eng.put(glv, load_vector(eng.get(disp_new)))
+                        else:
+                            eng.zero(glv)                                         # gravity is added by the assembly
                         eng.assemble(glv, grav, tangent=True, disp=disp_new, Et_E=Et_E)
                         eng.residual(1.0, glv, zero, f)
                         eng.axpby(1.0, modf, 1.0, f)

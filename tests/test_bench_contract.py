@@ -40,3 +40,43 @@ def test_product_arm_needs_a_gpu():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--n", "2"],
                        capture_output=True, text=True, timeout=300)
     assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)
+
+
+def test_weak_scaling_meshes_keep_the_elements_per_rank():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.weak_cells(55, 1) == (55, 55, 55)
+    assert bench.weak_cells(55, 2) == (55, 55, 110)
+    assert bench.weak_cells(55, 4) == (55, 110, 110)
+    assert bench.weak_cells(55, 8) == (110, 110, 110)
+    for w in (1, 2, 4, 8):
+        nx, ny, nz = bench.weak_cells(7, w)
+        assert nx * ny * nz == w * 7 ** 3
+    with pytest.raises(SystemExit):
+        bench.weak_cells(55, 3)
+    # the weak mesh keeps the element size and the nominal strain of the cube
+    m1, _ = bench.workload(3)
+    m2, _ = bench.workload(3, bench.weak_cells(3, 2))
+    assert m2.ne == 2 * m1.ne
+    h1 = m1.nocoord[:, 0].max() / 3
+    assert abs(m2.nocoord[:, 0].max() / 3 - h1) < 1e-12 and abs(m2.nocoord[:, 2].max() / 6 - h1) < 1e-12
+    top1 = max(v for v in m1.fix.values())
+    top2 = max(v for v in m2.fix.values())
+    assert abs(top2 / m2.nocoord[:, 2].max() - top1 / m1.nocoord[:, 2].max()) < 1e-15
+
+
+def test_check_object_compares_with_the_committed_single_gpu_trace(tmp_path, monkeypatch):
+    sys.path.insert(0, ROOT)
+    import types
+
+    import numpy as np
+
+    import bench
+    ref = json.load(open(os.path.join(ROOT, "profiles", "check_n55.json")))
+    a = types.SimpleNamespace(n=55, write_check=False, rtol=1e-8, steps=10, warmup=3)
+    sw = types.SimpleNamespace(errors=list(ref["newton_residual_trace"][:13]))
+    out = dict(iters=np.array(ref["newton_iters_per_step"]), lout=np.array(ref["lout"]), un=np.array(ref["un"]))
+    chk = bench.sweep_check(a, 4, None, sw, out)
+    assert chk["vs_single_gpu"]["ok"] and chk["vs_single_gpu"]["residual_trace_rel_diff"] == 0.0
+    out["lout"] = out["lout"] * (1 + 1e-5)
+    assert not bench.sweep_check(a, 4, None, sw, out)["vs_single_gpu"]["ok"]
