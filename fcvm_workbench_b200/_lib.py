@@ -92,6 +92,7 @@ _SIGNATURES = {
     "fcvm_profile_get": [ctxp, c_int, f64p, i64p],
     "fcvm_profile_reset": [ctxp],
     "fcvm_profile_seen": [ctxp, c_int],
+    "fcvm_copy_bytes": [ctxp, i64p, i64p],
     "fcvm_matrix_stats": [ctxp, i64p, i64p, i64p],
     "fcvm_last_error": [],
     "fcvm_version": [],

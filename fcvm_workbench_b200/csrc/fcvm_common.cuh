@@ -79,6 +79,7 @@ struct fcvm_ctx {
   std::vector<fcvm::ProfSample> prof_pool;
   size_t prof_used = 0;
   int64_t launches = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by fcvm_h2d / fcvm_d2h and the fcvm_host_* entry points
 
   // mesh
   int64_t ne = 0, nn = 0;

@@ -430,6 +430,12 @@ extern "C" int fcvm_synchronize(fcvm_ctx *c) {
 extern "C" int64_t fcvm_num_elements(const fcvm_ctx *c) { return c ? c->ne : 0; }
 extern "C" int64_t fcvm_num_nodes(const fcvm_ctx *c) { return c ? c->nn : 0; }
 extern "C" int64_t fcvm_launch_count(fcvm_ctx *c) { return c ? c->launches : 0; }
+extern "C" int fcvm_copy_bytes(fcvm_ctx *c, int64_t *h2d, int64_t *d2h) {
+  FCVM_CHECK(c, FCVM_E_ARG, "null context");
+  if (h2d) *h2d = c->h2d_bytes;
+  if (d2h) *d2h = c->d2h_bytes;
+  return FCVM_OK;
+}
 
 static int bits_for(uint64_t n) {
   int b = 1;
@@ -788,6 +794,7 @@ extern "C" int fcvm_h2d(fcvm_ctx *c, void *dst, const void *src, int64_t bytes) 
   FCVM_CHECK(c && dst && src && bytes >= 0, FCVM_E_ARG, "fcvm_h2d: bad argument");
   FCVM_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
   FCVM_CUDA(cudaStreamSynchronize(c->stream));
+  c->h2d_bytes += bytes;
   return FCVM_OK;
 }
 
@@ -795,6 +802,7 @@ extern "C" int fcvm_d2h(fcvm_ctx *c, void *dst, const void *src, int64_t bytes) 
   FCVM_CHECK(c && dst && src && bytes >= 0, FCVM_E_ARG, "fcvm_d2h: bad argument");
   FCVM_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
   FCVM_CUDA(cudaStreamSynchronize(c->stream));
+  c->d2h_bytes += bytes;
   return FCVM_OK;
 }
 

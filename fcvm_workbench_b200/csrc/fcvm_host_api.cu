@@ -90,6 +90,8 @@ extern "C" int fcvm_host_update_stress_load(fcvm_ctx *c, const double *sig_yield
   FCVM_CUDA(cudaMemcpyAsync(qin, c->h_qin, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
   FCVM_CUDA(cudaStreamSynchronize(st));
   FCVM_CUDA(cudaStreamSynchronize(c->h_out_stream));
+  c->h2d_bytes += (int64_t)sizeof(double) * (28 * ne + (disp_new ? 3 : 2) * n3);
+  c->d2h_bytes += (int64_t)sizeof(double) * (48 * ne + n3) + 4 * ne;
   return FCVM_OK;
 }
 

@@ -462,6 +462,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(call("fcvm_launch_count", self._ctx))
 
+    def copy_bytes(self):
+        """(host->device, device->host) bytes this engine's context has moved so far, counted in the library."""
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        call("fcvm_copy_bytes", self._ctx, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
     def deflation_stats(self):
         a, b = ctypes.c_int64(), ctypes.c_int64()
         call("fcvm_deflation_stats", self._ctx, ctypes.byref(a), ctypes.byref(b))

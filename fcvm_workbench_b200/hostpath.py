@@ -61,8 +61,7 @@ class HostEngine:
         self._pinned = []
         self._tviews = {}
         self.host_seconds = {}
-        self.h2d_bytes = 0
-        self.d2h_bytes = 0
+        self._bytes0 = self.dev.copy_bytes()
         ne = self.ne
         self._gp = {}
         for w in _GP6:
@@ -77,6 +76,15 @@ class HostEngine:
             self._set_masks()
 
     # -- memory ---------------------------------------------------------------------------------
+    # PCIe traffic of this engine, counted inside the library where the copies are issued
+    @property
+    def h2d_bytes(self):
+        return self.dev.copy_bytes()[0] - self._bytes0[0]
+
+    @property
+    def d2h_bytes(self):
+        return self.dev.copy_bytes()[1] - self._bytes0[1]
+
     def _alloc(self, n: int) -> np.ndarray:
         p = ctypes.c_void_p()
         call("fcvm_host_alloc", 8 * int(n), ctypes.byref(p))
@@ -260,8 +268,6 @@ class HostEngine:
     def solve(self, b, x, rtol=1e-10, max_iter=20000, use_x0=False, raise_on_noconv=True, recycle=False):
         """x = factor(b) (fcVM.py:1130, 1401): one h2d of b, PCG on the device, one d2h of x."""
         self.dev.host_solve(b, rtol, max_iter, out=x, raise_on_noconv=raise_on_noconv, recycle=recycle)
-        self.h2d_bytes += b.nbytes
-        self.d2h_bytes += x.nbytes
         self.last_solve = self.dev.last_solve
         return self.last_solve
 
@@ -273,9 +279,6 @@ class HostEngine:
         qin[:] = 0.0                                                     # the reference passes zeros (fcVM.py:1324)
         self.dev.host_update_stress_load(sy, disp_new, du, g[_fc.SIG_OLD], g[_fc.SIG_NEW], g[_fc.SIG_TEST], qin,
                                          Et_E, LD, self._pgp)
-        ne, nd = self.ne, self.ndof
-        self.h2d_bytes += 8 * (4 * ne + 24 * ne + 2 * nd + (nd if disp_new is not None else 0))
-        self.d2h_bytes += 8 * (48 * ne + nd) + 4 * ne
 
     @_timed
     def update_peeq_csr(self, ultimate_strain, Et_E):
@@ -283,8 +286,6 @@ class HostEngine:
         res = _fc.update_PEEQ_CSR(self.ne, None, g[_fc.SIG_TEST], g[_fc.SIG_NEW], g[_fc.SIG_YIELD], ultimate_strain,
                                   g[_fc.PEEQ], g[_fc.CSR], g[_fc.TRIAX], g[_fc.PRESSURE], g[_fc.SIGMISES],
                                   g[_fc.ECR], Et_E, engine=self.dev)
-        self.h2d_bytes += 8 * (48 + 12) * self.ne
-        self.d2h_bytes += 8 * 28 * self.ne
         return res
 
     def map_stresses(self, averaged, sig_yield, noce=None):

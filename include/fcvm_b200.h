@@ -253,6 +253,9 @@ int fcvm_profile_get(fcvm_ctx *ctx, int which, double *ms, int64_t *launches);
 int fcvm_profile_reset(fcvm_ctx *ctx);
 int64_t fcvm_profile_seen(fcvm_ctx *ctx, int which);
 int64_t fcvm_launch_count(fcvm_ctx *ctx);
+/* Bytes this context has moved host->device / device->host (fcvm_h2d, fcvm_d2h, fcvm_gp_*, fcvm_host_*), counted
+ * where the copies are issued. */
+int fcvm_copy_bytes(fcvm_ctx *ctx, int64_t *h2d, int64_t *d2h);
 
 /* Matrix storage facts for roofline arithmetic: stored 3x3 blocks (incl. padding) and real blocks. */
 int fcvm_matrix_stats(fcvm_ctx *ctx, int64_t *blocks_stored, int64_t *blocks_real, int64_t *bytes);
