@@ -191,8 +191,7 @@ struct fcvm_ctx {
   int64_t col0 = 0, col1 = 0;   // columns of E^-1 this rank's right-hand side can be non-zero in
   int64_t local_boxes = 0;      // boxes that hold nodes of this rank
   double *lam4 = nullptr;       // [4][6 ncl] column-quarter partials of E^-1 rhs
-  int32_t *wk_slice = nullptr;  // [workers + 1] slice range of every SpMV worker
-  int wk_grid = 0, wk_split = 0;
+  int wk_grid = 0, wk_split = 0;  // grid the fused kernel was prepared for, warps per SpMV worker
   double *fused_part = nullptr; // [4][grid] block partials of the in-kernel dot products
   unsigned long long *phase_ns = nullptr;   // [8] device time per phase of the fused kernel, [8] = iterations
   int fused_grid = 0;           // co-resident blocks of the fused kernel (0 = not yet queried)

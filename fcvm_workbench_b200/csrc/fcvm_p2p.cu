@@ -1,7 +1,8 @@
 // Peer-memory exchanges of the multi-GPU PCG iteration over NVLink / NVSwitch.
 //
 // One process per GPU; every rank owns an "arena" in device memory that its peers map through CUDA IPC.  An
-// exchange is ONE single-block kernel per rank that (1) stores its contribution straight into the peers' arenas
+// exchange is ONE kernel per rank (a single block for the small sums, a few blocks for the halo -- all resident
+// while they wait) that (1) stores its contribution straight into the peers' arenas
 // (st.global on mapped peer pointers), (2) publishes an epoch flag with release semantics at system scope,
 // (3) spins on its own flags until every contributor's epoch has arrived (acquire), and (4) combines the
 // contributions in ascending rank order -- so every rank computes bit-identical sums and takes the same

@@ -1,13 +1,16 @@
 // Block-SELL SpMV and the on-device preconditioned conjugate-gradient solve that replaces
 // factor = cholesky(gsm); x = factor(b)   (fcVM.py:1121-1135, 1264-1278, 1369-1406).
 //
-// Single-reduction (Chronopoulos-Gear) preconditioned CG: per iteration one SpMV w = K u -- which also
-// leaves the partial sums of w.u (and r.u) -- and one vector kernel (k_pcg_step).  The loop runs without
-// host round trips: step lengths live in device scalars, every dot product is a fixed-shape reduction
-// (bit-reproducible), and a device flag turns the remaining launches of a batch into no-ops once the
-// tolerance is met; the host only polls every CHECK_EVERY iterations.  Preconditioner: block-Jacobi, plus
-// the rigid-body-mode deflation level of fcvm_deflation.cu when switched on.  On a partitioned mesh the
-// interface exchange of w overlaps the interior part of the product (communication stream).
+// Single-reduction (Chronopoulos-Gear) preconditioned CG: per iteration one product w = K u -- which also
+// leaves the partial sums of w.u (and r.u) -- and one vector kernel (k_pcg_step_bulk: a bulk-copy stream; k_pcg_step
+// for unaligned or tiny problems).  The product is matrix-free (fcvm_matfree.cu) while the matrix is calcGSM's
+// elastic one, else the block-SELL SpMV below.  The loop runs without host round trips: step lengths live in
+// device scalars, every dot product is a fixed-shape reduction (bit-reproducible), and a device flag turns the
+// remaining launches of a batch into no-ops once the tolerance is met; the host only polls every CHECK_EVERY
+// iterations.  Preconditioner: block-Jacobi, plus the rigid-body-mode deflation level of fcvm_deflation.cu when
+// switched on.  Start vector: zero, the caller's, or the projection onto the last two solutions (use_x0 = 2).  On a
+// partitioned mesh the ranks exchange through mapped peer memory (fcvm_p2p.cu); without it the interface
+// all-reduce of w overlaps the interior part of the SpMV on a communication stream (NCCL).
 #include <cmath>
 
 #include "fcvm_common.cuh"

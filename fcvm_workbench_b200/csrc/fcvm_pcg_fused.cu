@@ -10,7 +10,7 @@
 //                coarse finish     chunk partials -> right-hand side of the coarse problem
 //                coarse product    lam = E^-1 rhs, rows x column quarters over the warps          (streams E^-1)
 //                expand            u = y + Z lam
-//   product      w = K u on the block-SELL matrix, static slice ranges per worker (1..8 warps)  (streams K)
+//   product      w = K u on the block-SELL matrix, slices dealt round by round to workers of 1..8 warps (streams K)
 //                + block partials of w.u and r.u
 //   step         p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; y = D^-1 r ; partials of r.r
 //
@@ -46,7 +46,7 @@ struct FusedArgs {
   int64_t nn, nslices;
   int max_iter, defl, split;
   // matrix (never written here)
-  const int32_t *slice_ptr, *slot_node, *colidx, *wk_slice;
+  const int32_t *slice_ptr, *slot_node, *colidx;
   const double *vals, *minv, *wt;
   // vectors (read and written across phases: plain pointers, no read-only path)
   double *x, *r, *u, *p, *s, *w;
@@ -422,10 +422,12 @@ bool coarse_fp32() {
   return v;
 }
 
-// Opt-in (FCVM_PCG_FUSED=1): measured on B200 at 1M elements the persistent kernel is correct (the whole GPU suite
-// passes with it) but slower than one launch per phase -- 16 resident warps per SM at the 128 registers its
-// largest phase needs do not keep enough loads in flight (product 0.53 ms against 0.46 ms for the dedicated
-// kernel at 48 warps per SM, coarse phases 1.5-2.5x); profiles/README.md has the numbers.
+// Opt-in (FCVM_PCG_FUSED=1), an EXPERIMENT kept for the record: measured on B200 at 1M elements the persistent
+// kernel is correct (the whole GPU suite passed with it) but slower than one launch per phase -- 16 resident warps
+// per SM at the 128 registers its largest phase needs do not keep enough loads in flight (product 0.53 ms against
+// 0.46 ms for the dedicated kernel at 48 warps per SM, coarse phases 1.5-2.5x); profiles/README.md has the numbers.
+// It applies the assembled operator and predates the matrix-free product and the bulk-copy kernels of the
+// production path.
 bool pcg_fused_enabled(const fcvm_ctx *c) {
   static const bool on = getenv("FCVM_PCG_FUSED") && atoi(getenv("FCVM_PCG_FUSED")) != 0;
   return on && c->world == 1;
@@ -493,8 +495,7 @@ void fused_free(fcvm_ctx *c) {
 }
 
 void fused_free_mesh(fcvm_ctx *c) {
-  cudaFree(c->wk_slice); cudaFree(c->fused_part);
-  c->wk_slice = nullptr;
+  cudaFree(c->fused_part);
   c->fused_part = nullptr;
   c->wk_grid = c->wk_split = 0;
 }
@@ -514,27 +515,13 @@ static int fused_prepare(fcvm_ctx *c) {
     c->fused_grid = per_sm * sms;
   }
   const int G = c->fused_grid;
-  if (!c->wk_slice || c->wk_grid != G) {
-    // static slice ranges of the SpMV workers, balanced by stored block columns; 1..8 warps per worker so that
-    // every worker still walks several slices when a rank holds few rows
+  if (c->wk_grid != G) {
+    // 1..8 warps per SpMV worker so that every worker still walks several slices when a rank holds few rows
+    // (slices are dealt to the workers round by round inside the kernel)
     int split = 8;
     for (int s = 1; s <= 8; s *= 2)
       if (c->nslices >= 6 * (int64_t)G * (FW / s)) { split = s; break; }
     if (getenv("FCVM_FUSED_SPLIT")) split = std::max(1, std::min(8, atoi(getenv("FCVM_FUSED_SPLIT"))));   // experiments
-    const int nwk = G * (FW / split);
-    std::vector<int32_t> sp((size_t)c->nslices + 1), wk((size_t)nwk + 1);
-    FCVM_CUDA(cudaMemcpy(sp.data(), c->slice_ptr, sizeof(int32_t) * (c->nslices + 1), cudaMemcpyDeviceToHost));
-    const int64_t total = sp[(size_t)c->nslices] + c->nslices;      // one unit per slice for its fixed cost
-    int64_t s = 0;
-    for (int k = 0; k < nwk; k++) {
-      wk[(size_t)k] = (int32_t)s;
-      const int64_t target = total * (k + 1) / nwk;
-      while (s < c->nslices && sp[(size_t)s + 1] + (s + 1) <= target) s++;
-    }
-    wk[(size_t)nwk] = (int32_t)c->nslices;
-    wk[0] = 0;
-    FCVM_TRY(realloc_dev(&c->wk_slice, nwk + 1));
-    FCVM_CUDA(cudaMemcpy(c->wk_slice, wk.data(), sizeof(int32_t) * (nwk + 1), cudaMemcpyHostToDevice));
     FCVM_TRY(realloc_dev(&c->fused_part, 4 * (int64_t)G));
     c->wk_grid = G;
     c->wk_split = split;
@@ -557,7 +544,7 @@ int pcg_fused_loop(fcvm_ctx *c, double *x, int max_iter) {
   a.max_iter = max_iter;
   a.defl = c->defl_ready ? 1 : 0;
   a.split = c->wk_split;
-  a.slice_ptr = c->slice_ptr; a.slot_node = c->slot_node; a.colidx = c->colidx; a.wk_slice = c->wk_slice;
+  a.slice_ptr = c->slice_ptr; a.slot_node = c->slot_node; a.colidx = c->colidx;
   a.vals = c->vals; a.minv = c->minv; a.wt = c->dof_weight;
   a.x = x; a.r = c->pcg_r; a.u = c->pcg_z; a.p = c->pcg_p; a.s = c->pcg_s; a.w = c->pcg_q;
   a.part = c->fused_part;
