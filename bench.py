@@ -178,7 +178,6 @@ class Sweep:
         self.errors = []
         self.bytes0 = (0, 0)
         self.prof = None
-        self.phases = ({}, 0)
 
     def _sync(self):
         self.eng.synchronize()
@@ -195,7 +194,6 @@ class Sweep:
             self._sync()
             if self.stride:
                 dev.profile(self.stride)
-            dev.pcg_phase_times(reset=True)
             self.bytes0 = (getattr(self.eng, "h2d_bytes", 0), getattr(self.eng, "d2h_bytes", 0))
             self.launch0 = dev.launch_count()
             self.t0 = time.time()
@@ -207,7 +205,6 @@ class Sweep:
             self.ms = dev.timer_stop_ms()
             self.t1 = time.time()
             self.launch1 = dev.launch_count()
-            self.phases = dev.pcg_phase_times()
             self.bytes1 = (getattr(self.eng, "h2d_bytes", 0), getattr(self.eng, "d2h_bytes", 0))
             if self.stride:
                 self.prof = dev.profile_get()
@@ -574,8 +571,6 @@ def main():
             "kernels": kern,
             "kernels_standalone": extra,
             "check": check,
-            "pcg_phases_ms_per_iteration": ({k: round(v / max(sw.phases[1], 1), 5) for k, v in sw.phases[0].items()}
-                                            if sw.phases[1] else None),
             "cpu_baseline": cb,
             "clocks": clk,
             "setup_s": {"mesh": round(t_mesh, 2)},

@@ -67,7 +67,6 @@ _SIGNATURES = {
     "fcvm_set_deflation": [ctxp, c_int, c_int, c_int, POINTER(ctypes.c_int32), f64p, f64p, u8p],
     "fcvm_deflation_stats": [ctxp, i64p, i64p],
     "fcvm_pcg_solve": [ctxp, c_void_p, c_void_p, c_double, c_int, c_int, POINTER(c_int), f64p],
-    "fcvm_pcg_phase_times": [ctxp, f64p, i64p, c_int],
     "fcvm_update_stress_load": [ctxp, c_void_p, c_void_p, c_void_p, c_double, c_int, c_double],
     "fcvm_update_peeq_csr": [ctxp, c_double, c_double, i64p, f64p],
     "fcvm_scale_step_stress": [ctxp, c_double],

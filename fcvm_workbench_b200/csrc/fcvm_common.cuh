@@ -178,23 +178,13 @@ struct fcvm_ctx {
   double *dE = nullptr, *dEinv = nullptr;             // [6 ncl][6 ncl]
   double *d_rhs = nullptr, *d_lam = nullptr;          // [6 ncl]
   double *spmv_part2 = nullptr; // per-slice partials of r.u
-  // fused (persistent, cooperative) PCG kernel: chunked coarse work lists, single-precision copies of the
-  // coarse operators (they only shape the preconditioner), slice ranges of the SpMV workers
-  int32_t *it_box = nullptr, *it_lo = nullptr, *it_hi = nullptr, *box_item_ptr = nullptr;
-  uint8_t *it_kind = nullptr;
-  int64_t n_items = 0;
-  double *item_part = nullptr;  // [n_items][6]
+  // single-precision copies of the coarse operators (they only shape the preconditioner)
   float *kz32 = nullptr;        // [18][nent]
   float *einv32 = nullptr;      // [6 ncl][einv_ld]
   int64_t einv_ld = 0;          // row stride of einv32: 6 ncl rounded up to 4 floats, padding zero
   double *rhs_part = nullptr;   // [RHS_SPLIT][6 ncl] shares of the coarse right-hand side
   int64_t col0 = 0, col1 = 0;   // columns of E^-1 this rank's right-hand side can be non-zero in
   int64_t local_boxes = 0;      // boxes that hold nodes of this rank
-  double *lam4 = nullptr;       // [4][6 ncl] column-quarter partials of E^-1 rhs
-  int wk_grid = 0, wk_split = 0;  // grid the fused kernel was prepared for, warps per SpMV worker
-  double *fused_part = nullptr; // [4][grid] block partials of the in-kernel dot products
-  unsigned long long *phase_ns = nullptr;   // [8] device time per phase of the fused kernel, [8] = iterations
-  int fused_grid = 0;           // co-resident blocks of the fused kernel (0 = not yet queried)
   void *cusolver = nullptr;
   double *cus_work = nullptr;
   int cus_lwork = 0;

@@ -353,12 +353,10 @@ void p2p_free(fcvm_ctx *c);
 int matfree_set_constraints(fcvm_ctx *c);
 int matfree_set_mesh(fcvm_ctx *c);
 void deflation_free(fcvm_ctx *c);
-void fused_free_mesh(fcvm_ctx *c);
 }
 
 static void free_mesh(fcvm_ctx *c) {
   deflation_free(c);
-  fused_free_mesh(c);
   dfree(c->conn); dfree(c->xyz); dfree(c->n2e_ptr); dfree(c->n2e_idx); dfree(c->elv);
   dfree(c->fixmask); dfree(c->fixval); dfree(c->movmask);
   for (int i = 0; i < FCVM_BUF_COUNT; i++) {
@@ -397,7 +395,6 @@ extern "C" int fcvm_destroy(fcvm_ctx *c) {
   if (c->cusolver) cusolverDnDestroy((cusolverDnHandle_t)c->cusolver);
   if (c->cus_work) cudaFree(c->cus_work);
   if (c->cus_info) cudaFree(c->cus_info);
-  if (c->phase_ns) cudaFree(c->phase_ns);
   if (c->h_in_stream) cudaStreamDestroy(c->h_in_stream);
   if (c->h_out_stream) cudaStreamDestroy(c->h_out_stream);
   for (int i = 0; i < 16; i++) {

@@ -359,6 +359,19 @@ __global__ void k_expand(int64_t nn, Grid g, const int32_t *__restrict__ cid, co
   }
 }
 
+__global__ void k_to_float(int64_t n, const double *__restrict__ src, float *__restrict__ dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+
+// rows of n doubles -> rows of ld floats, padding zero
+__global__ void k_to_float_rows(int64_t n, int64_t ld, const double *__restrict__ src, float *__restrict__ dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * ld) return;
+  const int64_t r = i / ld, q = i - r * ld;
+  dst[i] = q < n ? (float)src[r * n + q] : 0.0f;
+}
+
 template <typename T>
 int dalloc2(T **p, int64_t n) {
   if (*p) cudaFree(*p);
@@ -440,10 +453,25 @@ extern "C" int fcvm_deflation_stats(fcvm_ctx *c, int64_t *boxes, int64_t *entrie
 
 namespace fcvm {
 
-int fused_build_items(fcvm_ctx *c, const std::vector<int32_t> &cl_ptr, const std::vector<int32_t> &ent_ptr);
-int fused_refresh_coarse(fcvm_ctx *c);
-void fused_free(fcvm_ctx *c);
-bool coarse_fp32();
+// K Z and E^-1 are streamed in single precision by default (they only shape the preconditioner);
+// FCVM_COARSE_FP64=1 keeps the double-precision copies (comparison runs)
+bool coarse_fp32() {
+  static const bool v = !(getenv("FCVM_COARSE_FP64") && atoi(getenv("FCVM_COARSE_FP64")) != 0);
+  return v;
+}
+
+// single-precision copies of K Z and E^-1 (values change with every assembly); rows of E^-1 padded to 16 bytes
+static int refresh_coarse_fp32(fcvm_ctx *c) {
+  if (!coarse_fp32()) return FCVM_OK;
+  const int64_t nkz = 18 * c->nent, n6 = 6 * c->ncl, ne = n6 * c->einv_ld;
+  if (!c->kz32) FCVM_CUDA(cudaMalloc((void **)&c->kz32, sizeof(float) * (size_t)std::max<int64_t>(nkz, 1)));
+  if (!c->einv32) FCVM_CUDA(cudaMalloc((void **)&c->einv32, sizeof(float) * (size_t)std::max<int64_t>(ne, 1)));
+  k_to_float<<<grid_for(nkz, 256), 256, 0, c->stream>>>(nkz, c->kz_val, c->kz32);
+  k_to_float_rows<<<grid_for(ne, 256), 256, 0, c->stream>>>(n6, c->einv_ld, c->dEinv, c->einv32);
+  c->launches += 2;
+  FCVM_CUDA(cudaGetLastError());
+  return FCVM_OK;
+}
 bool p2p_ready(const fcvm_ctx *c);
 int p2p_allreduce_sum(fcvm_ctx *c, double *v, int64_t n, const double *sc, int done_slot);
 
@@ -509,9 +537,6 @@ int deflation_build(fcvm_ctx *c) {
     FCVM_CUDA(cudaMemcpy(c->ent_ptr, ptr.data(), sizeof(int32_t) * (ncl + 1), cudaMemcpyHostToDevice));
     FCVM_CUDA(cudaMemcpy(c->ent, ent_node.data(), sizeof(int32_t) * nent, cudaMemcpyHostToDevice));
     FCVM_CUDA(cudaMemcpy(c->ent_inv, inv.data(), sizeof(int32_t) * 8 * nn, cudaMemcpyHostToDevice));
-    std::vector<int32_t> clp((size_t)ncl + 1);
-    FCVM_CUDA(cudaMemcpy(clp.data(), c->cl_ptr, sizeof(int32_t) * (ncl + 1), cudaMemcpyDeviceToHost));
-    FCVM_TRY(fused_build_items(c, clp, ptr));
     cudaFree(c->kz32); cudaFree(c->einv32);       // sized by nent / ncl: reallocated by the refresh below
     c->kz32 = c->einv32 = nullptr;
     c->defl_structure = true;
@@ -553,7 +578,7 @@ int deflation_build(fcvm_ctx *c) {
   k_mirror<<<grid_for(n6 * n6, 256), 256, 0, st>>>(n6, c->dE, c->dEinv);
   FCVM_CUDA(cudaGetLastError());
   c->launches += 5;
-  FCVM_TRY(fused_refresh_coarse(c));
+  FCVM_TRY(refresh_coarse_fp32(c));
   c->defl_ready = true;
   return FCVM_OK;
 }
@@ -633,7 +658,8 @@ int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const doubl
 }
 
 void deflation_free(fcvm_ctx *c) {
-  fused_free(c);
+  cudaFree(c->kz32); cudaFree(c->einv32);
+  c->kz32 = c->einv32 = nullptr;
   cudaFree(c->cl_active); c->cl_active = nullptr;
   cudaFree(c->d_cid); cudaFree(c->cl_ptr); cudaFree(c->cl_nodes); cudaFree(c->kz_rel); cudaFree(c->kz_val);
   cudaFree(c->ent_ptr); cudaFree(c->ent); cudaFree(c->ent_inv); c->ent_inv = nullptr; cudaFree(c->dE); cudaFree(c->dEinv); cudaFree(c->d_rhs); cudaFree(c->d_lam);

@@ -1,5 +1,5 @@
 // Box-cluster geometry of the rigid-body-mode deflation level, shared by the set-up kernels
-// (fcvm_deflation.cu) and the fused PCG kernel (fcvm_pcg_fused.cu).
+// and the per-iteration kernels (fcvm_deflation.cu).
 #pragma once
 
 #include "fcvm_common.cuh"

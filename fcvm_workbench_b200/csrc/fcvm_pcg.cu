@@ -446,8 +446,6 @@ int launch_matfree(fcvm_ctx *c, const double *x, double *y, const double *sc, in
 bool p2p_ready(const fcvm_ctx *c);
 int p2p_halo(fcvm_ctx *c, double *v, double *sc, int gamma_slot, int rr_slot, bool with_scalars, bool done_check);
 int p2p_check(fcvm_ctx *c);
-bool pcg_fused_enabled(const fcvm_ctx *c);
-int pcg_fused_loop(fcvm_ctx *c, double *x, int max_iter);
 int interface_sum_on_comm_stream(fcvm_ctx *c, double *v);
 int comm_allreduce_on(fcvm_ctx *c, double *dev, int64_t n, cudaStream_t st);
 int deflation_correct(fcvm_ctx *c, const double *r, const double *y, const double *base, double *out, const double *sc,
@@ -656,22 +654,8 @@ extern "C" int fcvm_pcg_solve(fcvm_ctx *c, const double *b, double *x, double rt
     }
   }
   int it = 0, n_it = -1;
-  const bool fused = pcg_fused_enabled(c);
-  if (fused) {
-    // the whole loop in one persistent cooperative kernel (fcvm_pcg_fused.cu)
-    ProfScope ps(c, 3);
-    FCVM_TRY(pcg_fused_loop(c, x, max_iter));
-  } else {
-    FCVM_TRY(spmv_dot(0));
-  }
-  if (fused) {
-    FCVM_CUDA(cudaGetLastError());
-    FCVM_CUDA(cudaMemcpyAsync(c->h_scalars, sc, sizeof(double) * 16, cudaMemcpyDeviceToHost, st));
-    FCVM_CUDA(cudaStreamSynchronize(st));
-    it = (int)c->h_scalars[S_ITERS];
-    if ((int)c->h_scalars[S_STATUS] == PCG_CONVERGED) n_it = it;
-  }
-  while (!fused && n_it < 0 && it < max_iter) {
+  FCVM_TRY(spmv_dot(0));
+  while (n_it < 0 && it < max_iter) {
     const int batch_end = std::min(max_iter, it + CHECK_EVERY);
     for (; it < batch_end; it++) {
       {

@@ -1,5 +1,5 @@
 // Device scalar slots of the PCG solve (ctx->red_out), shared by the launch-per-phase solver
-// (fcvm_pcg.cu) and the fused persistent kernel (fcvm_pcg_fused.cu).
+// (fcvm_pcg.cu) and its helpers.
 #pragma once
 
 namespace fcvm {

@@ -451,14 +451,6 @@ class Engine:
             out[k] = (ms.value, n.value, int(call("fcvm_profile_seen", self._ctx, i)))
         return out
 
-    def pcg_phase_times(self, reset=False):
-        """Device time of the fused PCG kernel per phase since the last reset (ms) and the iterations covered."""
-        ms = (ctypes.c_double * 6)()
-        n = ctypes.c_int64()
-        call("fcvm_pcg_phase_times", self._ctx, ms, ctypes.byref(n), 1 if reset else 0)
-        names = ("step", "coarse_partials", "coarse_rhs", "coarse_product", "expand", "spmv")
-        return {k: ms[i] for i, k in enumerate(names)}, n.value
-
     def launch_count(self) -> int:
         return int(call("fcvm_launch_count", self._ctx))
 

@@ -161,11 +161,6 @@ int fcvm_matfree_apply(fcvm_ctx *ctx, const double *x, double *y);
  * recursively updated residual satisfies ||r|| <= rtol * ||b||; returns FCVM_E_NOCONV after max_iter. */
 int fcvm_pcg_solve(fcvm_ctx *ctx, const double *b, double *x, double rtol, int max_iter, int use_x0, int *iters,
                    double *relres);
-/* The iteration loop runs as ONE persistent cooperative kernel (phases separated by grid barriers, no host round
- * trips).  Device time it spent per phase since the last reset, in ms: [0] vector step, [1] coarse partials
- * (streams K Z), [2] coarse right-hand side, [3] coarse product (streams E^-1), [4] expansion u = y + Z lam,
- * [5] product w = K u; *iterations = PCG iterations these cover. */
-int fcvm_pcg_phase_times(fcvm_ctx *ctx, double *ms6, int64_t *iterations, int reset);
 
 /* Second preconditioner level (optional): deflation of the rigid-body modes of box clusters of nodes.
  * The clusters form an ncx x ncy x ncz grid of boxes lo + (i,j,k)*h over the (global) bounding box;

@@ -10,7 +10,7 @@ import json,sys
 n,f=sys.argv[1],sys.argv[2]
 try:
     d=json.loads(open(f+".json").read().strip().splitlines()[-1])
-    print(n, "ms/step", round(d["ms_per_step"],2), "pcg its", d["pcg_iterations_per_step"], "phases", d.get("pcg_phases_ms_per_iteration"), {k:(v.get("avg_ms"),v.get("launches")) for k,v in d["kernels"].items()})
+    print(n, "ms/step", round(d["ms_per_step"],2), "pcg its", d["pcg_iterations_per_step"], {k:(v.get("avg_ms"),v.get("launches")) for k,v in d["kernels"].items()})
 except Exception as e:
     print(n, "failed", e, open(f+".err").read()[-800:])
 P
