@@ -35,6 +35,9 @@ def main(argv=None):
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--gpus", type=int, default=1, help="GPUs of this box: the mesh is partitioned element-wise, one "
                                                         "process per GPU (launched through torch.distributed.run)")
+    ap.add_argument("--partition", choices=("auto", "slab", "compact"), default="auto",
+                    help="with --gpus: contiguous ranges of the element list as it is (slab) or after coordinate "
+                         "bisection (compact); auto = slab for --cube, compact for meshes read from a file")
     ap.add_argument("--quiet", action="store_true")
     a = ap.parse_args(argv)
 
@@ -84,7 +87,10 @@ def main(argv=None):
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        part = partition.slab_partition(m, world)
+        # structured cubes list their elements slab by slab; anything read from a file is renumbered by
+        # coordinate bisection first, so that a rank has a few neighbours instead of all of them
+        how = a.partition if a.partition != "auto" else ("compact" if (a.fcstd or a.npz) else "slab")
+        part = (partition.compact_partition if how == "compact" else partition.slab_partition)(m, world)
         comm = partition.Comm(part, rank, world)
         res = fcVM.calcDisp(part.local_model(rank), ctl, clicks=clicks, device=local, rtol=a.rtol, log=say, comm=comm,
                             deflation=deflation)
@@ -94,6 +100,7 @@ def main(argv=None):
         for key in ("stresses", "peeq", "sigmises", "csr"):
             res[key] = part.gather_gauss(comm.allgather(res[key]))
         # shared nodes carry the completed load on every rank that holds them: sum the gathered global vector
+        res["crip"] = part.original_gauss_point(res["crip"])
         res["loadsum"] = tuple(part.gather_nodal(comm.allgather(res["glv"])).reshape(-1, 3).sum(axis=0))
         dist.destroy_process_group()
         if rank != 0:

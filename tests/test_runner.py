@@ -62,8 +62,11 @@ def test_headless_runner_reproduces_the_reference_output_file(tmp_path):
     _check(*_run(tmp_path))
 
 
-def test_headless_runner_on_two_gpus(tmp_path):
+@pytest.mark.parametrize("how", ["slab", "compact"])
+def test_headless_runner_on_two_gpus(tmp_path, how):
+    """slab: ranges of the element list as it is; compact: after coordinate bisection, results restored to the
+    model's element order (partition.compact_partition -- the default for meshes read from a file)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    _check(*_run(tmp_path, ("--gpus", "2")))
+    _check(*_run(tmp_path, ("--gpus", "2", "--partition", how)))
