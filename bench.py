@@ -18,7 +18,7 @@ iterations of the sweep (the elastic first load step needs none and is passed be
 (``newton_iters_per_s`` and the raw stress-update rate are given beside it); ``e2e`` is the same
 sweep driven through the HOST-buffer C ABI (hostpath.HostEngine: numpy arrays in page-locked
 memory, every heavy call pays its PCIe copies).  What one PCG iteration streams (1.9 GB: element geometry,
-element vectors, work vectors, coarse operators) and the Gauss-point state of a Newton iteration (0.85 GB) are
+element vectors, work vectors, coarse operators) and the Gauss-point state of a Newton iteration (0.96 GB) are
 far larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
 
 For N > 1 (torchrun) the same 1M-element mesh is partitioned element-wise into N slabs (``--scaling strong``,
@@ -564,7 +564,7 @@ def main():
                                           if defl_grid else "block-Jacobi"),
                        "l2": "inputs exceed L2: per rank and PCG iteration %.2f GB of element geometry, element vectors, "
                              "work vectors and coarse operators, %.2f GB of Gauss-point state per Newton iteration, "
-                             "vs 126 MB" % (ne_total / world * 1.9e-6, ne_total / world * 0.85e-6)},
+                             "vs 126 MB" % (ne_total / world * 1.9e-6, ne_total / world * 0.96e-6)},
             "newton_iters_per_s": a.steps / (ms * 1e-3),
             "stress_update_gauss_points_per_s": gp_rate,
             "pcg_iterations_per_step": float(np.mean(sw.pcg_its)) if sw.pcg_its else None,
